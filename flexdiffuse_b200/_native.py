@@ -1,0 +1,262 @@
+'''ctypes binding of include/flexdiffuse_b200.h.
+
+This is the only place Python touches the C ABI.  There is no fallback: if the
+shared library is missing or a call returns non-zero, a `NativeError` is raised.
+Torch is used solely for device memory, streams and dtype bookkeeping.
+'''
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+LIB_NAME = 'libflexdiffuse_b200.so'
+LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
+
+FD_ABI_VERSION = 1
+FD_DTYPE_F32 = 0
+FD_DTYPE_BF16 = 1
+FD_BLEND_OK = 0
+FD_BLEND_ZERO_DIVISION = 1
+
+# every symbol include/flexdiffuse_b200.h declares (tests check they all export)
+ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
+               'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
+               'fd_kv_project', 'fd_cross_attn')
+
+
+class NativeError(RuntimeError):
+    '''A C-ABI call failed (or the library is not built).'''
+
+
+class SchedCoeffs(C.Structure):
+    '''struct fd_sched_coeffs'''
+    _fields_ = [('guidance', C.c_float), ('use_cfg', C.c_int),
+                ('w', C.c_float * 4), ('a', C.c_float), ('b', C.c_float),
+                ('c_noise', C.c_float), ('in_scale', C.c_float)]
+
+
+class TweenParams(C.Structure):
+    '''struct fd_tween_params'''
+    _fields_ = [('threshold_floor', C.c_double), ('threshold_mult', C.c_double),
+                ('clustered', C.c_double), ('max_guidance', C.c_double),
+                ('header_max', C.c_double), ('align_mode', C.c_int),
+                ('mapping_reuse', C.c_int)]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib() -> C.CDLL:
+    '''Load (once) and return the native library; raise loudly if absent.'''
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise NativeError(
+            f'{LIB_PATH} is not built. Run `python -m flexdiffuse_b200.build` '
+            '(needs nvcc). flexdiffuse_b200 has no CPU / PyTorch fallback.')
+    l = C.CDLL(str(LIB_PATH))
+    l.fd_version.restype = C.c_int
+    l.fd_last_error_string.restype = C.c_char_p
+    l.fd_arch_check.argtypes = [C.c_int]
+    l.fd_arch_check.restype = C.c_int
+    l.fd_sm_count.restype = C.c_int
+    vp = C.c_void_p
+    l.fd_cfg_sched_step.argtypes = [
+        vp, vp, C.c_int, vp, vp, vp, vp, vp,
+        C.POINTER(SchedCoeffs), C.c_int64, vp, vp, vp, C.c_int, vp
+    ]
+    l.fd_cfg_sched_step.restype = C.c_int
+    l.fd_sim_blend.argtypes = [
+        vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
+        vp, vp, vp, vp, vp, vp, vp
+    ]
+    l.fd_sim_blend.restype = C.c_int
+    l.fd_kv_project.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    l.fd_kv_project.restype = C.c_int
+    l.fd_cross_attn.argtypes = [
+        vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, C.c_int, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp
+    ]
+    l.fd_cross_attn.restype = C.c_int
+    if l.fd_version() != FD_ABI_VERSION:
+        raise NativeError(f'ABI mismatch: library {l.fd_version()} != '
+                          f'binding {FD_ABI_VERSION}; rebuild')
+    _lib = l
+    return l
+
+
+def last_error() -> str:
+    return lib().fd_last_error_string().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise NativeError(f'{what} failed (code {rc}): {last_error()}')
+
+
+def require_device(device: torch.device | int | None = None) -> None:
+    '''Raise unless `device` is an sm_100 GPU.  No fallback.'''
+    if device is None:
+        idx = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    elif isinstance(device, int):
+        idx = device
+    else:
+        idx = device.index if device.index is not None else (
+            torch.cuda.current_device() if torch.cuda.is_available() else 0)
+    check(lib().fd_arch_check(idx), 'fd_arch_check')
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return FD_DTYPE_F32
+    if dt == torch.bfloat16:
+        return FD_DTYPE_BF16
+    raise NativeError(f'unsupported dtype {dt} (need float32 or bfloat16)')
+
+
+def _need(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not t.is_cuda:
+        raise NativeError(
+            f'{name} must be a CUDA tensor (got {t.device}); flexdiffuse_b200 '
+            'has no CPU fallback')
+    if not t.is_contiguous():
+        raise NativeError(f'{name} must be contiguous')
+    if dtype is not None and t.dtype != dtype:
+        raise NativeError(f'{name} must be {dtype}, got {t.dtype}')
+
+
+# --------------------------------------------------------------------------- K4
+def cfg_sched_step(eps_uncond: Optional[torch.Tensor],
+                   eps_cond: torch.Tensor,
+                   x: torch.Tensor,
+                   coeffs: SchedCoeffs,
+                   x_out: torch.Tensor,
+                   hist: Sequence[torch.Tensor] = (),
+                   noise: Optional[torch.Tensor] = None,
+                   eps_out: Optional[torch.Tensor] = None,
+                   scaled_out: Optional[torch.Tensor] = None) -> None:
+    '''fd_cfg_sched_step on the current stream of `x.device`.'''
+    _need(eps_cond, 'eps_cond')
+    _need(x, 'x', torch.float32)
+    _need(x_out, 'x_out', torch.float32)
+    n = x.numel()
+    for name, t in (('eps_uncond', eps_uncond), ('noise', noise),
+                    ('eps_out', eps_out), ('scaled_out', scaled_out),
+                    *((f'hist[{i}]', h) for i, h in enumerate(hist))):
+        if t is not None:
+            _need(t, name)
+            if t.numel() != n:
+                raise NativeError(f'{name} has {t.numel()} elements, x has {n}')
+    if eps_cond.numel() != n or x_out.numel() != n:
+        raise NativeError('eps_cond / x_out size mismatch with x')
+    if eps_uncond is not None and eps_uncond.dtype != eps_cond.dtype:
+        raise NativeError('eps_uncond / eps_cond dtype mismatch')
+    for h in hist:
+        if h.dtype != torch.float32:
+            raise NativeError('history tensors must be float32')
+    if len(hist) > 3:
+        raise NativeError('at most 3 history tensors')
+    hp = [ptr(h) for h in hist] + [None] * (3 - len(hist))
+    rc = lib().fd_cfg_sched_step(
+        ptr(eps_uncond), ptr(eps_cond), dtype_code(eps_cond.dtype), ptr(x),
+        hp[0], hp[1], hp[2], ptr(noise), C.byref(coeffs), n, ptr(x_out),
+        ptr(eps_out), ptr(scaled_out),
+        dtype_code(scaled_out.dtype) if scaled_out is not None else FD_DTYPE_F32,
+        stream_ptr(x.device))
+    check(rc, 'fd_cfg_sched_step')
+
+
+# --------------------------------------------------------------------------- K1
+def sim_blend(text: torch.Tensor,
+              guide: torch.Tensor,
+              params: Sequence[TweenParams],
+              linear_weights: torch.Tensor,
+              want_sim: bool = False):
+    '''fd_sim_blend.  text [B,T,D] f32, guide [G,A,D] f32 (G in {1,B}),
+    linear_weights [P,T] f32 on the same device.
+    Returns dict(out [B,P,T,D], map_s [B,P,T], map_idx [B,P,T], weights [B,P,T],
+    status [B,P], sim [B,A,T] | None).'''
+    _need(text, 'text', torch.float32)
+    _need(guide, 'guide', torch.float32)
+    _need(linear_weights, 'linear_weights', torch.float32)
+    B, T, D = text.shape
+    G, A, D2 = guide.shape
+    P = len(params)
+    if D2 != D or G not in (1, B):
+        raise NativeError(f'guide shape {tuple(guide.shape)} incompatible with '
+                          f'text {tuple(text.shape)}')
+    if tuple(linear_weights.shape) != (P, T):
+        raise NativeError(f'linear_weights must be [{P},{T}]')
+    dev = text.device
+    out = torch.empty((B, P, T, D), dtype=torch.float32, device=dev)
+    map_s = torch.empty((B, P, T), dtype=torch.float32, device=dev)
+    map_idx = torch.empty((B, P, T), dtype=torch.int32, device=dev)
+    weights = torch.empty((B, P, T), dtype=torch.float32, device=dev)
+    status = torch.empty((B, P), dtype=torch.int32, device=dev)
+    sim = (torch.empty((B, A, T), dtype=torch.float32, device=dev)
+           if want_sim else None)
+    arr = (TweenParams * P)(*params)
+    params_dev = torch.frombuffer(bytearray(bytes(arr)),
+                                  dtype=torch.uint8).to(dev)
+    rc = lib().fd_sim_blend(ptr(text), ptr(guide), B, G, T, A, D,
+                            ptr(params_dev),
+                            ptr(linear_weights), P, ptr(out), ptr(map_s),
+                            ptr(map_idx), ptr(weights), ptr(status), ptr(sim),
+                            stream_ptr(dev))
+    check(rc, 'fd_sim_blend')
+    return dict(out=out, map_s=map_s, map_idx=map_idx, weights=weights,
+                status=status, sim=sim)
+
+
+# --------------------------------------------------------------------------- K2
+def kv_project(ctx: torch.Tensor, w: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    '''fd_kv_project: out[M,N] = ctx[M,K] @ w[N,K]^T, all bf16.'''
+    _need(ctx, 'ctx', torch.bfloat16)
+    _need(w, 'w', torch.bfloat16)
+    M, K = ctx.shape
+    N, K2 = w.shape
+    if K2 != K:
+        raise NativeError('ctx / w inner dimension mismatch')
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=ctx.device)
+    _need(out, 'out', torch.bfloat16)
+    rc = lib().fd_kv_project(ptr(ctx), ptr(w), ptr(out), M, N, K,
+                             stream_ptr(ctx.device))
+    check(rc, 'fd_kv_project')
+    return out
+
+
+# --------------------------------------------------------------------------- K3
+def cross_attn(q: torch.Tensor, kv: torch.Tensor, k_col_off: int,
+               v_col_off: int, ctx_index: torch.Tensor, heads: int,
+               t_valid: int, t_pad: int, scale: float,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    '''fd_cross_attn: q [S,Nq,C] bf16, kv = K2 output [n_ctx*t_pad, N] bf16.'''
+    _need(q, 'q', torch.bfloat16)
+    _need(kv, 'kv', torch.bfloat16)
+    _need(ctx_index, 'ctx_index', torch.int32)
+    S, Nq, Cc = q.shape
+    if Cc % heads:
+        raise NativeError('channels not divisible by heads')
+    if out is None:
+        out = torch.empty_like(q)
+    _need(out, 'out', torch.bfloat16)
+    rc = lib().fd_cross_attn(ptr(q), ptr(kv), kv.shape[0], kv.shape[1],
+                             k_col_off, v_col_off, ptr(ctx_index), S, Nq, heads,
+                             Cc // heads, t_valid, t_pad, float(scale),
+                             ptr(out), stream_ptr(q.device))
+    check(rc, 'fd_cross_attn')
+    return out

@@ -1,0 +1,174 @@
+// K2 -- cross-attention K/V projection of the fixed 77-token context, hoisted out of the
+// denoising loop: ONE batched GEMM per prompt batch instead of 32 small Linears x 16 layers x
+// every step (diffusers CrossAttention.forward `to_k(context)`, `to_v(context)`, reached from
+// pipeline/guide.py:56-58).
+//
+//   out[M, N] = ctx[M, K] . w[N, K]^T      bf16 operands, fp32 accumulate, bf16 out
+//   M = n_ctx * 80 (context rows, zero padded 77 -> 80), K = 768, N = 24960 (all to_k|to_v rows)
+//
+// Warp-specialised tcgen05 GEMM: warp 0 = TMA producer (SWIZZLE_128B K-major tiles),
+// warp 1 = single-thread tcgen05.mma issuer (accumulator 128x128 fp32 in TMEM),
+// warps 2-5 = epilogue (tcgen05.ld -> bf16 -> global).  4-stage mbarrier ring.
+// Grid: m-tile fastest so the CTAs sharing one weight tile run together (weight tile read from
+// HBM once, the other m-tiles hit L2).
+#include "fd_common.cuh"
+
+namespace fd {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int K2_THREADS = 192;
+constexpr int K2_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*bars*/;
+
+__global__ void __launch_bounds__(K2_THREADS, 1)
+k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+               __nv_bfloat16* __restrict__ out, int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_blk = blockIdx.x;
+  const int n_blk = blockIdx.y;
+  const int num_kb = K / BK;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tm_a, &full_bar[s], kb * BK, m_blk * BM);
+        tma_load_2d(smem_b + s * B_STAGE_BYTES, &tm_b, &full_bar[s], kb * BK, n_blk * BN);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, BM, BN, 0, 0);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES), 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
+          mma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+        }
+        tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+      }
+      tc_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    const int quarter = warp & 3;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = quarter * 32 + lane;
+    const int64_t g_row = static_cast<int64_t>(m_blk) * BM + row;
+    const int n0 = n_blk * BN;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, v);
+      tmem_ld_wait();
+      if (g_row < M) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        }
+        __nv_bfloat16* dst = out + g_row * N + n0 + c;
+        if (n0 + c + 8 <= N) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (n0 + c + 16 <= N) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, void* out_bf16_dev,
+                             int M, int N, int K, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(ctx_bf16_dev && w_bf16_dev && out_bf16_dev, "fd_kv_project: NULL pointer");
+  FD_REQUIRE(M > 0 && N > 0 && K > 0, "fd_kv_project: non-positive shape %d %d %d", M, N, K);
+  FD_REQUIRE(K % BK == 0, "fd_kv_project: K=%d must be a multiple of %d", K, BK);
+  FD_REQUIRE(N % 8 == 0, "fd_kv_project: N=%d must be a multiple of 8", N);
+  FD_REQUIRE(reinterpret_cast<uintptr_t>(ctx_bf16_dev) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(w_bf16_dev) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(out_bf16_dev) % 16 == 0,
+             "fd_kv_project: pointers must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != FD_OK) return rc;
+
+  CUtensorMap tm_a, tm_b;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BK, BM};
+    rc = encode_tmap(&tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ctx_bf16_dev, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BK, BN};
+    rc = encode_tmap(&tm_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_bf16_dev, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+  }
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
+    attr_set = true;
+  }
+  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
+  k2_gemm_kernel<<<grid, K2_THREADS, K2_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      tm_a, tm_b, static_cast<__nv_bfloat16*>(out_bf16_dev), M, N, K);
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
+}

@@ -1,0 +1,181 @@
+/*
+ * flexdiffuse_b200 -- C ABI of the B200 (sm_100a) hot path of tim-speed/flexdiffuse.
+ *
+ * The reference is pure Python and has no FFI of its own, so
+ * every entry point below cites the reference *Python* call site whose arithmetic it
+ * replaces.  The host-side mirror of the reference API (flexdiffuse_b200/guidance.py,
+ * pipeline/guide.py, pipeline/flex.py) binds these with ctypes; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every `*_dev` pointer is DEVICE memory owned by the caller, outputs are
+ *     caller-allocated;  pointers without the suffix are HOST memory;
+ *   - all launches are asynchronous on the caller-supplied `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream);
+ *   - re-entrant, no global mutable state besides a thread-local error string;
+ *   - return value 0 = success, negative = error (see fd_last_error_string()).
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute
+ *     entry point returns FD_ERR_ARCH.
+ */
+#ifndef FLEXDIFFUSE_B200_H
+#define FLEXDIFFUSE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_ABI_VERSION 1
+
+/* error codes */
+#define FD_OK            0
+#define FD_ERR_ARG      -1   /* bad argument (shape, alignment, null pointer)       */
+#define FD_ERR_ARCH     -2   /* no CUDA device / device is not sm_100               */
+#define FD_ERR_CUDA     -3   /* a CUDA runtime / driver call failed                 */
+#define FD_ERR_UNSUPP   -4   /* shape outside what the kernels were built for       */
+
+/* element types */
+#define FD_DTYPE_F32   0
+#define FD_DTYPE_BF16  1
+
+/* guide orders -- guidance.py:18-20 */
+#define FD_GUIDE_ORDER_TEXT    0
+#define FD_GUIDE_ORDER_ALIGN   1
+#define FD_GUIDE_ORDER_DIRECT  2
+
+/* per-blend status word written by fd_sim_blend */
+#define FD_BLEND_OK            0
+#define FD_BLEND_ZERO_DIVISION 1   /* two adjacent similarity peaks: the reference raises
+                                      ZeroDivisionError in guidance.py:111-112 */
+
+/* ---- library ----------------------------------------------------------------------- */
+
+/* ABI version of the loaded library (== FD_ABI_VERSION of the header it was built from). */
+int fd_version(void);
+
+/* Thread-local, human readable description of the last error on this thread. */
+const char* fd_last_error_string(void);
+
+/* 0 when `device` exists and is compute capability 10.x, FD_ERR_ARCH otherwise.
+ * Never falls back to anything: the Python host raises on non-zero. */
+int fd_arch_check(int device);
+
+/* Number of SMs of the current device (grid sizing / bench reporting), <0 on error. */
+int fd_sm_count(void);
+
+/* ---- K4: classifier-free-guidance combine + scheduler update ------------------------ *
+ * Replaces  pipeline/guide.py:61-63   eps = u + g * (c - u)
+ *      and  the diffusers `scheduler.step(...)` called at pipeline/flex.py:280-285
+ *      and  the LMS model-input pre-scale at pipeline/flex.py:270-274.
+ * One vectorised elementwise pass:
+ *      eps   = use_cfg ? u + g * (c - u) : c
+ *      e'    = w[0]*eps + w[1]*h1 + w[2]*h2 + w[3]*h3        (PLMS / LMS multistep mix)
+ *      x'    = a * x + b * e' + c_noise * noise             (DDIM / PLMS / LMS update)
+ *      eps_out    = eps                 (optional, history for the multistep schedulers)
+ *      scaled_out = x' * in_scale       (optional, next step's model input; bf16 or f32)
+ * The scalar coefficients are computed on the host in fp64 by the scheduler state
+ * machine (flexdiffuse_b200/schedulers.py) and rounded to fp32 here, as the reference's
+ * Python-float * fp32-tensor products are.                                              */
+typedef struct fd_sched_coeffs {
+  float guidance;    /* g                                                    */
+  int   use_cfg;     /* pipeline/guide.py:47  (guidance > 1.0)               */
+  float w[4];        /* multistep weights; unused history => 0 and NULL ptr  */
+  float a;           /* sample coefficient                                   */
+  float b;           /* model-output coefficient                             */
+  float c_noise;     /* DDIM eta>0 variance noise coefficient (0 = no noise) */
+  float in_scale;    /* scaled_out = x' * in_scale                           */
+} fd_sched_coeffs;
+
+int fd_cfg_sched_step(const void*  eps_uncond_dev,  /* [n] eps_dtype, may be NULL when !use_cfg */
+                      const void*  eps_cond_dev,    /* [n] eps_dtype                            */
+                      int          eps_dtype,       /* FD_DTYPE_F32 | FD_DTYPE_BF16             */
+                      const float* x_dev,           /* [n] current latents (or PLMS cur_sample) */
+                      const float* h1_dev,          /* [n] history t-1 or NULL                  */
+                      const float* h2_dev,          /* [n] history t-2 or NULL                  */
+                      const float* h3_dev,          /* [n] history t-3 or NULL                  */
+                      const float* noise_dev,       /* [n] or NULL                              */
+                      const fd_sched_coeffs* coeffs,/* HOST pointer, copied at launch           */
+                      int64_t      n_elem,          /* multiple of 4                            */
+                      float*       x_out_dev,       /* [n] may alias x_dev                      */
+                      float*       eps_out_dev,     /* [n] or NULL                              */
+                      void*        scaled_out_dev,  /* [n] scaled_dtype or NULL                 */
+                      int          scaled_dtype,
+                      void*        stream);
+
+/* ---- K1: text-token x guide-token similarity map + re-weighting + blend ------------- *
+ * Replaces  guidance.py:23-85    _map_emb            (normalise, 100*cos, softmax over the
+ *                                                     text tokens, header column dropped,
+ *                                                     per-mode / reuse assignment)
+ *           guidance.py:135-172  _clustered_guidance (+ _traverse_a_to_b :88-132)
+ *           guidance.py:175-193  _blend_weights
+ *           guidance.py:215-272  Tweener.tween       (avg similarity, threshold weights,
+ *                                                     header cap, 3-way select / lerp)
+ * for `n_text` prompts against one shared guide (guide_batch == 1) or one guide per
+ * prompt (guide_batch == n_text), and `n_params` parameter sets per prompt.
+ * The similarity GEMM runs on tcgen05 (kind::tf32, 3-pass hi/lo split => fp32-equivalent
+ * logits) with the accumulator in TMEM; softmax is per TMEM lane, the
+ * column arg-max and the weight heuristics are warp-shuffle code in the same kernel.   */
+typedef struct fd_tween_params {
+  double threshold_floor;   /* Tweener.threshold_floor   guidance.py:205 */
+  double threshold_mult;    /* Tweener.threshold_mult    guidance.py:206 */
+  double clustered;         /* Tweener.clustered         guidance.py:209 */
+  double max_guidance;      /* Tweener.max_guidance      guidance.py:210 */
+  double header_max;        /* Tweener.header_max        guidance.py:211 */
+  int    align_mode;        /* FD_GUIDE_ORDER_*          guidance.py:212 */
+  int    mapping_reuse;     /* bool                      guidance.py:213 */
+} fd_tween_params;
+
+int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddings             */
+                 const float* guide_dev,     /* [guide_batch, A, D] fp32 alt embeddings          */
+                 int n_text, int guide_batch,
+                 int T,                      /* text tokens  (77; 2 <= T <= 80)                  */
+                 int A,                      /* guide tokens (257 image / 77 text; 1 <= A <= 384)*/
+                 int D,                      /* embedding width (768; multiple of 32)            */
+                 const fd_tween_params* params_dev, /* DEVICE [n_params] (8-byte aligned)           */
+                 const float* linear_weights_dev,   /* [n_params, T] torch.linspace, gd.py:231   */
+                 int n_params,
+                 float*   out_dev,           /* [n_text, n_params, T, D] blended embeddings      */
+                 float*   map_s_dev,         /* [n_text, n_params, T] similarity s  (or NULL)    */
+                 int32_t* map_idx_dev,       /* [n_text, n_params, T] guide index   (or NULL)    */
+                 float*   weights_dev,       /* [n_text, n_params, T] final alt_weights (or NULL)*/
+                 int32_t* status_dev,        /* [n_text, n_params] FD_BLEND_*                    */
+                 float*   sim_dev,           /* [n_text, A, T] softmax matrix P (debug, or NULL) */
+                 void* stream);
+
+/* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
+ * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'
+ * CrossAttention.forward recomputes for each of the 16 attn2 layers at every step,
+ * reached from pipeline/guide.py:56-58.   out[M,N] = ctx[M,K] . w[N,K]^T   (bf16 in,
+ * fp32 accumulate in TMEM, bf16 out) -- TMA-fed tcgen05 GEMM.  `w` is the row-wise
+ * concatenation of all to_k / to_v weights (N = 2 * sum(C_l) = 24960 for SD v1).        */
+int fd_kv_project(const void* ctx_bf16_dev,  /* [M, K] row-major bf16, M = n_ctx * T_pad */
+                  const void* w_bf16_dev,    /* [N, K] row-major bf16                     */
+                  void*       out_bf16_dev,  /* [M, N] row-major bf16                     */
+                  int M, int N, int K,       /* K % 64 == 0, N % 8 == 0                   */
+                  void* stream);
+
+/* ---- K3: cross-attention over the cached K/V ----------------------------------------- *
+ * Replaces diffusers' CrossAttention._attention (softmax(Q K^T * scale) V over the 77
+ * context tokens, no mask), reached from pipeline/guide.py:56-58 for each attn2 layer.
+ * q / out are [n_samples, n_q, heads*d_head] bf16; K and V are column slices of the
+ * K2 output: for sample s, rows ctx_index[s]*t_pad .. +t_pad-1, columns
+ * k_col_off + h*d_head .. and v_col_off + h*d_head ..                                   */
+int fd_cross_attn(const void* q_bf16_dev,
+                  const void* kv_bf16_dev,      /* K2 output [n_ctx*t_pad, kv_row_stride]  */
+                  int64_t kv_rows,              /* n_ctx * t_pad                            */
+                  int64_t kv_row_stride,        /* elements per cache row (N of K2)         */
+                  int k_col_off, int v_col_off, /* element offsets, multiples of 8          */
+                  const int32_t* ctx_index_dev, /* [n_samples] context id of each sample    */
+                  int n_samples, int n_q, int heads, int d_head, /* d_head in {40,80,160}   */
+                  int t_valid,                  /* 77: keys >= t_valid are masked           */
+                  int t_pad,                    /* 80                                       */
+                  float scale,                  /* d_head ** -0.5                           */
+                  void* out_bf16_dev,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLEXDIFFUSE_B200_H */

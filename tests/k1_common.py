@@ -1,0 +1,78 @@
+'''Helpers shared by the K1 parity tests: run fd_sim_blend through the C ABI and
+check it against the oracle (oracle/guidance_oracle.py).
+
+Methodology: the blended output is piecewise constant in the
+similarity values, and fp32 re-orderings of the 768-term dot product move the
+similarities by ~1e-6.  So parity is split in two exact statements:
+  (1) the similarity matrix P from the tcgen05 3xTF32 GEMM + softmax matches the
+      oracle's fp32 P within SIM_RTOL / SIM_ATOL;
+  (2) every discrete decision and every output bit the kernel derives from ITS P
+      equals what the oracle derives from the same P (bit-exact).
+plus (3) end to end against the oracle's own P: rows whose decisions agree are
+bit-identical, and rows that differ are provable near-ties.'''
+import numpy as np
+import torch
+
+from oracle import guidance_oracle as orc
+
+SIM_RTOL, SIM_ATOL = 2e-4, 2e-6
+TIE_REL = 1e-4  # decisions closer than this (relative) may flip
+
+
+def to_native_params(native, prm: orc.TweenParams):
+    p = native.TweenParams()
+    p.threshold_floor, p.threshold_mult = prm.threshold
+    p.clustered = prm.clustered
+    p.max_guidance = prm.max_guidance
+    p.header_max = prm.header_max
+    p.align_mode = prm.align_mode
+    p.mapping_reuse = int(prm.mapping_reuse)
+    return p
+
+
+def run_kernel(native, dev, txt, img, prms, want_sim=True):
+    T = txt.shape[1]
+    lin = torch.stack([
+        torch.linspace(p.linear[0], p.linear[1], steps=T) for p in prms
+    ]).to(dev)
+    res = native.sim_blend(txt.to(dev).contiguous(), img.to(dev).contiguous(),
+                           [to_native_params(native, p) for p in prms], lin,
+                           want_sim=want_sim)
+    torch.cuda.synchronize()
+    return {k: (v.cpu() if v is not None else None) for k, v in res.items()}
+
+
+def oracle_from_P(P: torch.Tensor, txt, img, prm: orc.TweenParams):
+    '''Oracle decisions + output given a similarity matrix P [A,T] (fp32).'''
+    mapped = orc.map_from_similarity(P.double().numpy(), txt.shape[1],
+                                     prm.mapping_reuse, prm.align_mode)
+    try:
+        w = orc.tween_weights(mapped, prm)
+    except ZeroDivisionError:
+        return dict(zde=True, mapped=mapped)
+    sel, iw = orc.tween_select(mapped, w, prm.max_guidance)
+    idx = torch.from_numpy(mapped[:, 0].astype(np.int64))
+    a, b = img[0, idx], txt[0]
+    lerp = b + (a - b) * torch.tensor(iw).to(torch.float32)[:, None]
+    s = torch.from_numpy(sel)[:, None]
+    out = torch.where(s == 0, b, torch.where(s == 1, a, lerp))
+    return dict(zde=False, mapped=mapped, w=w, sel=sel, iw=iw, out=out)
+
+
+def check_exact_given_P(res, bi, pi, txt_b, img_b, prm):
+    '''Statement (2): kernel decisions == oracle decisions on the kernel's P.'''
+    P = res['sim'][bi]
+    o = oracle_from_P(P, txt_b, img_b, prm)
+    status = int(res['status'][bi, pi])
+    if o['zde']:
+        assert status == 1, 'oracle raises ZeroDivisionError, kernel did not'
+        return 'zde'
+    assert status == 0, 'kernel flagged ZeroDivision, oracle did not'
+    np.testing.assert_array_equal(res['map_idx'][bi, pi].numpy(),
+                                  o['mapped'][:, 0].astype(np.int32))
+    np.testing.assert_array_equal(res['map_s'][bi, pi].double().numpy(),
+                                  o['mapped'][:, 1])
+    assert torch.equal(res['weights'][bi, pi], o['w']), (
+        res['weights'][bi, pi] - o['w']).abs().max()
+    assert torch.equal(res['out'][bi, pi], o['out'])
+    return 'ok'
