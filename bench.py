@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+'''bench.py -- FlexDiffuse hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): SD1.5 512^2 50-step images/s (+ guided-embed blends/s, % roofline).
+Workload at every N: BASELINE.json configs[1] -- SD v1.5 UNet 512x512, 50-step DDIM, CFG 7.5,
+text-only conditioning, batch 1 per GPU, random-init weights, synthetic prompt embeddings.
+
+One bench "step" = one pass of the hot path over one batch: K2 K/V cache build, 50 denoising
+steps (UNet forward over cached K/V with K3, then the fused CFG+DDIM K4), VAE decode.
+
+  value : whole-job images/s with every input already resident in HBM (device-timed)
+  e2e   : same metric through the public API (SimpleGuide + FlexPipeline) with HOST inputs:
+          per step the prompt/uncond embeddings and the initial noise are copied from pinned
+          host memory and the decoded image is read back (those bytes are reported)
+  roofline     : K3 cross-attention (the dominant hand-written kernel of a step), timed
+                 live with CUDA events on the launching stream; K4 / K2 / K1 alongside
+  cpu_baseline : the oracle port of the reference path (fp32, all host cores) on a bounded
+                 sample of the same workload, extrapolated as stated in `sample`
+  --impl reference : only that CPU arm, as its own JSON line
+'''
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STEPS_PER_IMAGE = 50
+GUIDANCE = 7.5
+HW = 512
+METRIC = 'sd15_512x512_50step_ddim_cfg7.5_images_per_s'
+UNIT = 'images/s'
+WORKLOAD = ('SD v1.5 UNet 512x512, 50-step DDIM, CFG 7.5, text-only conditioning, '
+            'batch 1 per GPU, random-init weights (BASELINE.json configs[1])')
+
+
+def _peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p['hbm_gbs'], tensor=p['bf16_tflops'],
+                    tensor_sustained=p.get('bf16_tflops_sustained'),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0,
+                source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    '''nvidia-smi clocks / throttle reasons sampled DURING the timed region.'''
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx or None,
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ------------------------------------------------------------------ reference / CPU arm
+def cpu_reference_arm(steps: int, warmup: int):
+    '''The reference's path on the host cores: the oracle port (fp32 restatement of
+    pipeline/flex.py + pipeline/guide.py over diffusers' UNet arithmetic).  Each bench step is
+    a BOUNDED sample: 1 of the 50 DDIM steps at B=1 (2 UNet sample-forwards + CFG + scheduler
+    update); images/s = 1 / (50 * t_step).  VAE decode (~1.5 % of the FLOPs) excluded.'''
+    from flexdiffuse_b200.unet import UNet2DConditionModel
+    from oracle import loop_oracle as lo
+    from oracle import unet_oracle as U
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    with torch.no_grad():
+        sd = {k: v.float() for k, v in UNet2DConditionModel().state_dict().items()}
+        g = torch.Generator().manual_seed(0)
+        uncond = torch.randn(1, 77, 768, generator=g)
+        embeds = torch.randn(1, 77, 768, generator=g)
+        x = torch.randn(1, 4, HW // 8, HW // 8, generator=g)
+        sched = lo.DDIMScheduler()
+        sched.set_timesteps(STEPS_PER_IMAGE)
+        ts = [int(t) for t in sched.timesteps]
+
+        def one(i):
+            eps = lo.noise_pred(lambda l, t, c: U.unet_forward(sd, l, t, c), uncond,
+                                embeds, GUIDANCE, x, ts[i % len(ts)])
+            return sched.step(eps, ts[i % len(ts)], x).prev_sample
+
+        for i in range(warmup):
+            one(i)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            one(i)
+        dt = (time.perf_counter() - t0) / max(steps, 1)
+    value = 1.0 / (STEPS_PER_IMAGE * dt)
+    return dict(value=value, unit=UNIT, cores=cores, kind='port',
+                sample=(f'{steps} x [1 of 50 DDIM steps at B=1: 2 fp32 UNet sample-forwards '
+                        f'+ CFG + scheduler step] = {dt:.2f} s/step on {cores} threads; '
+                        'images/s = 1/(50*t_step); VAE decode excluded')), dt
+
+
+def cpu_blend_baseline(n: int = 8):
+    '''Reference blend (guidance.py Tweener.tween) via the oracle port, blends/s.'''
+    from oracle import guidance_oracle as orc
+    txt, img = orc.synthetic_pair(0, planted=12)
+    prm = orc.TweenParams(clustered=0.0)
+    orc.tween(txt, img, prm)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        orc.tween(txt, img, prm)
+    return n / (time.perf_counter() - t0)
+
+
+# ------------------------------------------------------------------ kernel microbenches
+def _time_cuda(fn, iters, flush=None):
+    st = torch.cuda.current_stream()
+    times = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.add_(1.0)  # > L2: evict everything between timed launches
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn()
+        b.record(st)
+        b.synchronize()
+        times.append(a.elapsed_time(b) * 1e-3)
+    return sum(times) / len(times)
+
+
+def kernel_rooflines(dev, unet, peaks):
+    '''Live CUDA-event timings of the hand-written kernels against their rooflines.'''
+    from flexdiffuse_b200 import _native
+    from flexdiffuse_b200 import schedulers
+    out = {}
+    flush = torch.empty(96 * 1024 * 1024, dtype=torch.float32, device=dev)  # 384 MB
+    # ---- K3: all 16 attn2 sites of one UNet forward, 8 samples (inputs >> L2 are streamed)
+    S = 8
+    ctx = torch.randn(2, 77, 768, device=dev)
+    kv = unet.build_kv_cache(ctx)
+    idx = torch.tensor([0] * (S // 2) + [1] * (S // 2), dtype=torch.int32, device=dev)
+    sites, alg_bytes, alg_flops = [], 0, 0
+    for m in unet.cross_attentions():
+        n_q = {320: 4096, 640: 1024, 1280: 256}[m.dim]
+        sites.append((m, torch.randn(S, n_q, m.dim, device=dev).bfloat16()))
+    sites[6] = (sites[6][0], sites[6][1][:, :64].contiguous())  # mid block: 8x8 latent
+    outs = [torch.empty_like(q) for _, q in sites]
+    for m, q in sites:
+        alg_bytes += 2 * q.numel() * 2 + 2 * 80 * m.dim * 2 * 2  # Q in + O out + K,V (2 ctx)
+        alg_flops += 4 * q.shape[0] * q.shape[1] * 77 * m.dim
+
+    def run_k3():
+        for (m, q), o in zip(sites, outs):
+            _native.cross_attn(q, kv.kv, m.k_col_off, m.v_col_off, idx, m.heads, 77, 80,
+                               m.scale, out=o)
+
+    run_k3()
+    # the 16 launches are replayed from a CUDA graph so host launch latency is not timed
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        run_k3()
+    torch.cuda.current_stream().wait_stream(side)
+    g3 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g3):
+        run_k3()
+    t = _time_cuda(g3.replay, 10, flush)
+    out['k3'] = dict(bound='hbm', achieved=alg_bytes / t / 1e9, peak=peaks['hbm'],
+                     unit='GB/s', frac=alg_bytes / t / 1e9 / peaks['hbm'], traffic=None,
+                     kernel='k3_cross_attn_kernel (16 attn2 sites, 8 samples)',
+                     launches=16, avg_launch_us=t / 16 * 1e6,
+                     tflops=alg_flops / t / 1e12, peak_of=peaks['source'])
+    # ---- K4: fused CFG + DDIM step, 1024 samples fp32 (268 MB algorithmic traffic > L2)
+    B = 1024
+    n = B * 4 * 64 * 64
+    u, c, x = (torch.randn(n, device=dev) for _ in range(3))
+    xo = torch.empty_like(x)
+    k = _native.SchedCoeffs()
+    k.guidance, k.use_cfg, k.a, k.b = 7.5, 1, 1.01, -0.05
+    k.w[0] = 1.0
+    f4 = lambda: _native.cfg_sched_step(u, c, x, k, xo)
+    f4()
+    t = _time_cuda(f4, 20)
+    out['k4'] = dict(bound='hbm', achieved=16 * n / t / 1e9, peak=peaks['hbm'], unit='GB/s',
+                     frac=16 * n / t / 1e9 / peaks['hbm'], traffic=None,
+                     kernel='k4_cfg_sched_kernel (DDIM, fp32, 1024 samples)',
+                     avg_launch_us=t * 1e6, peak_of=peaks['source'])
+    del u, c, x, xo
+    # ---- K2: K/V projection of 9 contexts (config 3), tensor bound
+    ctx9 = torch.randn(9, 77, 768, device=dev)
+    f2 = lambda: unet.build_kv_cache(ctx9)
+    f2()
+    t = _time_cuda(f2, 10, flush)
+    fl = 2 * 9 * 80 * 768 * 24960
+    out['k2'] = dict(bound='tensor', achieved=fl / t / 1e12, peak=peaks['tensor'],
+                     unit='TFLOP/s', frac=fl / t / 1e12 / peaks['tensor'], traffic=None,
+                     kernel='k2_gemm_kernel (M=720,N=24960,K=768; incl. bf16 pad copy)',
+                     avg_launch_us=t * 1e6, peak_of=peaks['source'])
+    # ---- K1: blends/s -- 1024 prompts x 1 shared guide image, default parameters
+    nb = 1024
+    txt = torch.randn(nb, 77, 768, device=dev)
+    img = torch.randn(1, 257, 768, device=dev)
+    prm = _native.TweenParams()
+    prm.threshold_floor = prm.threshold_mult = prm.max_guidance = 0.5
+    prm.clustered, prm.header_max, prm.align_mode, prm.mapping_reuse = 0.0, 0.15, 1, 1
+    lin = torch.linspace(0.0, 0.5, 77)[None].to(dev)
+    f1 = lambda: _native.sim_blend(txt, img, [prm], lin)
+    f1()
+    t = _time_cuda(f1, 5)
+    fl = 3 * 2 * 384 * 80 * 768 * nb   # 3-pass tf32, padded tiles
+    by = nb * (2 * 77 * 768 * 4) + 257 * 768 * 4
+    out['k1'] = dict(bound='hbm', achieved=by / t / 1e9, peak=peaks['hbm'], unit='GB/s',
+                     frac=by / t / 1e9 / peaks['hbm'], traffic=None,
+                     kernel='k1_sim_blend_kernel (1024 prompts x 1 guide)',
+                     blends_per_s=nb / t, issued_tf32_tflops=fl / t / 1e12,
+                     avg_launch_us=t * 1e6, peak_of=peaks['source'])
+    return out
+
+
+# ------------------------------------------------------------------ main arm
+class _Enc:
+    '''Stand-in for CLIPEncoder on the text-only workload: the CLIP towers stay in PyTorch
+    and are not part of configs[1]; prompt embeddings are synthetic.'''
+    def __init__(self, uncond):
+        self.uncond = uncond
+
+    def prompt(self, p):
+        return self.uncond
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=4)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-kernels', action='store_true', help='skip kernel microbenches')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        base, dt = cpu_reference_arm(max(args.steps, 1), min(args.warmup, 1))
+        print(json.dumps({
+            'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT,
+            'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 1),
+            'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD,
+                       'note': 'one bench step = a bounded sample (1 of 50 DDIM steps)'},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}))
+        return
+
+    from flexdiffuse_b200 import _native, factory, schedulers
+    from flexdiffuse_b200.pipeline.flex import FlexPipeline
+    from flexdiffuse_b200.pipeline.guide import SimpleGuide
+    _native.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    _native.require_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+    torch.backends.cudnn.benchmark = True
+    peaks = _peaks()
+
+    unet = factory.build_unet(dev, torch.bfloat16, seed=0)
+    vae = factory.build_vae(dev, torch.bfloat16, seed=1)
+    B = 1
+    g = torch.Generator().manual_seed(1234 + rank)
+    h_uncond = torch.randn(1, 77, 768, generator=g).pin_memory()
+    h_embeds = torch.randn(B, 77, 768, generator=g).pin_memory()
+    d_uncond, d_embeds = h_uncond.to(dev), h_embeds.to(dev)
+    noise_elems = B * 4 * (HW // 8) * (HW // 8)
+
+    pipe = FlexPipeline(vae, None, None, unet, schedulers.DDIMScheduler())
+
+    d_gen = torch.Generator(device=dev)
+    h_gen = torch.Generator()
+
+    def run_resident():
+        # every input already in HBM, result left in HBM
+        d_gen.manual_seed(99 + rank)
+        guide = SimpleGuide(_Enc(d_uncond), unet, GUIDANCE, STEPS_PER_IMAGE, d_embeds,
+                            use_cuda_graph=True)
+        return pipe(guide, init_size=(HW, HW), generator=d_gen, output_type='pt',
+                    return_dict=False)
+
+    def run_e2e():
+        # the call a user makes, from HOST buffers to a HOST image
+        h_gen.manual_seed(99 + rank)
+        uncond = h_uncond.to(dev, non_blocking=True)
+        embeds = h_embeds.to(dev, non_blocking=True)
+        guide = SimpleGuide(_Enc(uncond), unet, GUIDANCE, STEPS_PER_IMAGE, embeds,
+                            use_cuda_graph=True)
+        return pipe(guide, init_size=(HW, HW), generator=h_gen, output_type='np').images
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, sample_clocks=False):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        before = _native.LAUNCHES
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        if sampler:
+            sampler.__exit__()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms / steps, _native.LAUNCHES - before, (sampler.summary() if sampler else None)
+
+    W = max(args.warmup, 3)
+    ms_res, launches, clocks = timed(run_resident, args.steps, W, sample_clocks=True)
+    ms_e2e, _, _ = timed(run_e2e, args.steps, 1)
+
+    value = world * B / (ms_res * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': W, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'images_per_step_per_gpu': B,
+                   'parallelism': f'replicas x{world} (independent samples, no collective '
+                                  'in the loop)',
+                   'l2': 'working set (1.7 GB bf16 UNet weights streamed every denoising '
+                         'step) exceeds the 126 MB L2; no explicit flush',
+                   'cuda_graph': 'UNet forward captured once, replayed 50x per image'},
+        'e2e': {'value': e2e, 'unit': UNIT, 'ms_per_step': ms_e2e,
+                'h2d_bytes_per_step': int(h_uncond.numel() + h_embeds.numel() +
+                                          noise_elems) * 4,
+                'd2h_bytes_per_step': B * 3 * HW * HW * 4},
+        'gpu_launches': launches,
+        'clocks': clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_kernels:
+        kr = kernel_rooflines(dev, unet, peaks)
+        line['roofline'] = kr['k3']
+        line['roofline_k4'] = kr['k4']
+        line['roofline_k2'] = kr['k2']
+        line['roofline_k1'] = kr['k1']
+        base, _ = cpu_reference_arm(2, 1)
+        line['cpu_baseline'] = base
+        cb = cpu_blend_baseline()
+        line['blends'] = {'gpu_blends_per_s': kr['k1']['blends_per_s'],
+                          'cpu_blends_per_s': cb, 'cpu_kind': 'port',
+                          'cpu_cores': os.cpu_count(),
+                          'workload': '1 prompt [77,768] x 1 guide image [257,768], defaults '
+                                      '(BASELINE.json configs[0]); GPU batch 1024 prompts'}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

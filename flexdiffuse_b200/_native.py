@@ -48,6 +48,15 @@ class TweenParams(C.Structure):
 
 _lib: Optional[C.CDLL] = None
 
+# number of kernels of THIS library launched from this process (graph replays are added by
+# the caller that owns the graph); bench.py reports it as `gpu_launches`
+LAUNCHES = 0
+
+
+def count_launch(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 
 def lib() -> C.CDLL:
     '''Load (once) and return the native library; raise loudly if absent.'''
@@ -176,6 +185,7 @@ def cfg_sched_step(eps_uncond: Optional[torch.Tensor],
         dtype_code(scaled_out.dtype) if scaled_out is not None else FD_DTYPE_F32,
         stream_ptr(x.device))
     check(rc, 'fd_cfg_sched_step')
+    count_launch()
 
 
 # --------------------------------------------------------------------------- K1
@@ -216,6 +226,7 @@ def sim_blend(text: torch.Tensor,
                             ptr(map_idx), ptr(weights), ptr(status), ptr(sim),
                             stream_ptr(dev))
     check(rc, 'fd_sim_blend')
+    count_launch()
     return dict(out=out, map_s=map_s, map_idx=map_idx, weights=weights,
                 status=status, sim=sim)
 
@@ -236,6 +247,7 @@ def kv_project(ctx: torch.Tensor, w: torch.Tensor,
     rc = lib().fd_kv_project(ptr(ctx), ptr(w), ptr(out), M, N, K,
                              stream_ptr(ctx.device))
     check(rc, 'fd_kv_project')
+    count_launch()
     return out
 
 
@@ -259,4 +271,5 @@ def cross_attn(q: torch.Tensor, kv: torch.Tensor, k_col_off: int,
                              Cc // heads, t_valid, t_pad, float(scale),
                              ptr(out), stream_ptr(q.device))
     check(rc, 'fd_cross_attn')
+    count_launch()
     return out

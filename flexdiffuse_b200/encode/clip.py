@@ -1,0 +1,68 @@
+'''CLIP encoders -- API mirror of /root/reference/encode/clip.py.
+
+`preprocess` (clip.py:15-39) and `CLIPEncoder.prompt / .image` (clip.py:47-100) keep the
+reference's signatures and numerics.  The transformer towers stay in PyTorch
+(transformers' CLIPModel); BASELINE.json's north_star only moves the similarity /
+blend stage that consumes these embeddings onto hand-written kernels (K1).
+'''
+from __future__ import annotations
+
+from typing import Any, List
+
+import numpy as np
+import torch
+
+CLIP_IMAGE_SIZE = 224
+MAX_SINGLE_DIM = 512  # Stable Diffusion's native side length
+
+_CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+_CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+def preprocess(image: Any) -> torch.Tensor:
+    '''PIL image -> [1,3,h,w] float32 in [-1,1]; the longer side becomes 512, the
+    shorter one is scaled with it and floored to a multiple of 64 (clip.py:24-39).'''
+    from PIL.Image import LANCZOS
+    w, h = image.size
+    if h == w:
+        w = h = MAX_SINGLE_DIM
+    elif h > w:
+        w, h = (int(w / (h / MAX_SINGLE_DIM)) // 64) * 64, MAX_SINGLE_DIM
+    else:
+        h, w = (int(h / (w / MAX_SINGLE_DIM)) // 64) * 64, MAX_SINGLE_DIM
+    arr = np.array(image.resize((w, h), resample=LANCZOS).convert('RGB'))
+    arr = arr.astype(np.float32) / 255.0
+    return 2.0 * torch.from_numpy(arr[None].transpose(0, 3, 1, 2)) - 1.0
+
+
+class CLIPEncoder():
+    def __init__(self, clip, token) -> None:
+        self.clip = clip
+        self.token = token
+
+    def prompt(self, prompt: str | List[str]) -> torch.Tensor:
+        '''Final-layer-norm hidden states of the text tower, NOT projected
+        (clip.py:57-65): [B, 77, 768].'''
+        ids = self.token(prompt, padding='max_length',
+                         max_length=self.token.model_max_length,
+                         truncation=True, return_tensors='pt').input_ids
+        return self.clip.text_model(ids.to(self.clip.device))[0]
+
+    def image(self, image) -> torch.Tensor:
+        '''All 257 vision tokens through post_layernorm and visual_projection
+        (clip.py:76-100): [1, 257, 768].  Note the CLIP mean/std are applied to a
+        [-1,1] tensor, exactly as the reference does.'''
+        from torchvision.transforms.functional import (InterpolationMode,
+                                                       center_crop, normalize,
+                                                       resize)
+        x = preprocess(image)
+        side = min(x.shape[-2:])
+        x = center_crop(x, [side, side])
+        x = resize(x, [CLIP_IMAGE_SIZE, CLIP_IMAGE_SIZE],
+                   interpolation=InterpolationMode.BICUBIC, antialias=True)
+        x = normalize(x, list(_CLIP_MEAN), list(_CLIP_STD)).to(self.clip.device)
+        vm = self.clip.vision_model
+        hidden = vm.pre_layrnorm(vm.embeddings(x))
+        hidden = vm.encoder(inputs_embeds=hidden, output_attentions=False,
+                            output_hidden_states=False, return_dict=True)[0]
+        return self.clip.visual_projection(vm.post_layernorm(hidden))
