@@ -1,0 +1,97 @@
+'''Profiling target for ncu (run under gpurun, never a bench number):
+
+  ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \
+      --csv --log-file gpurun_out/launches.csv python profiles/prof_step.py step
+  ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -k regex:'k[1-4]_' -o gpurun_out/kernels python profiles/prof_step.py kernels
+
+`step`    : ONE denoising step of bench.py's workload (SD v1.5 UNet 512^2, B=1, CFG -> 2
+            sample-forwards, eager so every kernel is named) + the fused K4 DDIM update.
+`kernels` : the hand-written kernels at the sizes bench.py's roofline section uses.
+'''
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from flexdiffuse_b200 import _native, factory, schedulers  # noqa: E402
+from flexdiffuse_b200.pipeline.guide import SimpleGuide  # noqa: E402
+
+
+class Enc:
+    def __init__(self, u):
+        self.u = u
+
+    def prompt(self, p):
+        return self.u
+
+
+def main(mode: str):
+    dev = torch.device('cuda:0')
+    torch.backends.cudnn.benchmark = True
+    unet = factory.build_unet(dev, torch.bfloat16, seed=0)
+    g = torch.Generator(device=dev).manual_seed(0)
+    uncond = torch.randn(1, 77, 768, device=dev, generator=g)
+    embeds = torch.randn(1, 77, 768, device=dev, generator=g)
+    if mode == 'step':
+        guide = SimpleGuide(Enc(uncond), unet, 7.5, 50, embeds, use_cuda_graph=False)
+        sched = schedulers.DDIMScheduler()
+        sched.set_timesteps(50)
+        x = torch.randn(1, 4, 64, 64, device=dev, generator=g)
+        buf = guide.model_input_buffer(x)
+        buf.copy_(x)
+        ts = [int(t) for t in sched.timesteps]
+        for i in range(3):  # warm-up: cuDNN autotune, allocator
+            u, c = guide.noise_pred_pair(buf, ts[i])
+            x = sched.fused_step(u, c, 7.5, True, ts[i], x, scaled_out=buf).prev_sample
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        u, c = guide.noise_pred_pair(buf, ts[3])
+        x = sched.fused_step(u, c, 7.5, True, ts[3], x, scaled_out=buf).prev_sample
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    # ---- kernels
+    S = 8
+    ctx = torch.randn(2, 77, 768, device=dev, generator=g)
+    ctx9 = torch.randn(9, 77, 768, device=dev, generator=g)
+    kv = unet.build_kv_cache(ctx)
+    idx = torch.tensor([0] * 4 + [1] * 4, dtype=torch.int32, device=dev)
+    mods = unet.cross_attentions()
+    picks = [mods[0], mods[2], mods[4]]  # C = 320 / 640 / 1280
+    qs = [torch.randn(S, {320: 4096, 640: 1024, 1280: 256}[m.dim], m.dim, device=dev,
+                      generator=g).bfloat16() for m in picks]
+    n = 1024 * 4 * 64 * 64
+    u, c, x = (torch.randn(n, device=dev, generator=g) for _ in range(3))
+    xo = torch.empty_like(x)
+    k = _native.SchedCoeffs()
+    k.guidance, k.use_cfg, k.a, k.b = 7.5, 1, 1.01, -0.05
+    k.w[0] = 1.0
+    txt = torch.randn(1024, 77, 768, device=dev, generator=g)
+    img = torch.randn(1, 257, 768, device=dev, generator=g)
+    prm = _native.TweenParams()
+    prm.threshold_floor = prm.threshold_mult = prm.max_guidance = 0.5
+    prm.header_max, prm.align_mode, prm.mapping_reuse = 0.15, 1, 1
+    lin = torch.linspace(0.0, 0.5, 77)[None].to(dev)
+
+    def run():
+        for m, q in zip(picks, qs):
+            _native.cross_attn(q, kv.kv, m.k_col_off, m.v_col_off, idx, m.heads, 77, 80,
+                               m.scale)
+        _native.cfg_sched_step(u, c, x, k, xo)
+        unet.build_kv_cache(ctx9)
+        _native.sim_blend(txt, img, [prm], lin)
+
+    run()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    run()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if __name__ == '__main__':
+    main(sys.argv[1] if len(sys.argv) > 1 else 'step')
