@@ -329,13 +329,23 @@ def main():
     d_gen = torch.Generator(device=dev)
     h_gen = torch.Generator()
 
+    gathered = (torch.empty((world * B, 4, HW // 8, HW // 8), device=dev)
+                if world > 1 else None)
+
+    def collect(lat):
+        # the only collective of the path: gather the output latents of the sharded samples
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, lat.contiguous())
+
     def run_resident():
         # every input already in HBM, result left in HBM
         d_gen.manual_seed(99 + rank)
         guide = SimpleGuide(_Enc(d_uncond), unet, GUIDANCE, STEPS_PER_IMAGE, d_embeds,
                             use_cuda_graph=True)
-        return pipe(guide, init_size=(HW, HW), generator=d_gen, output_type='pt',
-                    return_dict=False)
+        lat = pipe(guide, init_size=(HW, HW), generator=d_gen, output_type='latent',
+                   return_dict=False)
+        collect(lat)
+        return pipe.decode(lat, 'pt')
 
     def run_e2e():
         # the call a user makes, from HOST buffers to a HOST image
@@ -344,7 +354,12 @@ def main():
         embeds = h_embeds.to(dev, non_blocking=True)
         guide = SimpleGuide(_Enc(uncond), unet, GUIDANCE, STEPS_PER_IMAGE, embeds,
                             use_cuda_graph=True)
-        return pipe(guide, init_size=(HW, HW), generator=h_gen, output_type='np').images
+        if world == 1:
+            return pipe(guide, init_size=(HW, HW), generator=h_gen, output_type='np').images
+        lat = pipe(guide, init_size=(HW, HW), generator=h_gen, output_type='latent',
+                   return_dict=False)
+        collect(lat)
+        return pipe.decode(lat, 'np')
 
     def barrier():
         torch.cuda.synchronize()
@@ -386,8 +401,9 @@ def main():
         'warmup': W, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
         'config': {'workload': WORKLOAD, 'images_per_step_per_gpu': B,
-                   'parallelism': f'replicas x{world} (independent samples, no collective '
-                                  'in the loop)',
+                   'parallelism': f'replicas x{world}: independent samples sharded over ranks, no '
+                                  'collective in the loop, one NCCL all-gather of the output '
+                                  'latents per step',
                    'l2': 'working set (1.7 GB bf16 UNet weights streamed every denoising '
                          'step) exceeds the 126 MB L2; no explicit flush',
                    'cuda_graph': 'UNet forward captured once, replayed 50x per image'},

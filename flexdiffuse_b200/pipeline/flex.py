@@ -201,26 +201,30 @@ class FlexPipeline():
         if output_type == 'latent':
             return latents if not return_dict else StableDiffusionPipelineOutput(
                 latents, [False] * latents.shape[0])
-        if output_type == 'pt':
-            # decoded images left on the device: [B,3,H,W] in [0,1]
-            image = self.vae.decode(1 / 0.18215 * latents).sample
-            image = (image / 2 + 0.5).clamp(0, 1)
-            return image if not return_dict else StableDiffusionPipelineOutput(
-                image, [False] * image.shape[0])
-        pil = output_type == 'pil'
         if all_latents:
-            batches = [self._latents_to_image(l, pil) for l in all_latents]
+            batches = [self.decode(l, output_type) for l in all_latents]
             if isinstance(batches[0], list):
                 batch_images = [im for b in batches for im in b]
+            elif torch.is_tensor(batches[0]):
+                batch_images = torch.cat(batches)
             else:
                 batch_images = np.concatenate(batches, axis=0)
         else:
-            batch_images = self._latents_to_image(latents, pil)
+            batch_images = self.decode(latents, output_type)
         if not return_dict:
             return (batch_images, False)
         return StableDiffusionPipelineOutput(
             images=batch_images,
             nsfw_content_detected=[False for _ in batch_images])
+
+    @torch.no_grad()
+    def decode(self, latents: torch.Tensor, output_type: str = 'pil'):
+        '''flex.py:112-124 for 'pil' / 'np'; 'pt' leaves the [B,3,H,W] images in [0,1] on the
+        device (no host copy).'''
+        if output_type == 'pt':
+            image = self.vae.decode(1 / 0.18215 * latents).sample
+            return (image / 2 + 0.5).clamp(0, 1)
+        return self._latents_to_image(latents, output_type == 'pil')
 
     def _fused_loop(self, guide, sched, latents, steps_ts, t_start, is_lms,
                     extra, generator, all_latents):
