@@ -24,7 +24,8 @@ FD_BLEND_ZERO_DIVISION = 1
 # every symbol include/flexdiffuse_b200.h declares (tests check they all export)
 ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
-               'fd_kv_project', 'fd_cross_attn')
+               'fd_kv_project', 'fd_cross_attn',
+               'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act', 'fd_geglu')
 
 
 class NativeError(RuntimeError):
@@ -91,6 +92,15 @@ def lib() -> C.CDLL:
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp
     ]
     l.fd_cross_attn.restype = C.c_int
+    l.fd_groupnorm_act_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    l.fd_groupnorm_act_workspace_bytes.restype = C.c_int
+    l.fd_groupnorm_act.argtypes = [
+        vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+        C.c_int, vp
+    ]
+    l.fd_groupnorm_act.restype = C.c_int
+    l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
+    l.fd_geglu.restype = C.c_int
     if l.fd_version() != FD_ABI_VERSION:
         raise NativeError(f'ABI mismatch: library {l.fd_version()} != '
                           f'binding {FD_ABI_VERSION}; rebuild')
@@ -271,5 +281,50 @@ def cross_attn(q: torch.Tensor, kv: torch.Tensor, k_col_off: int,
                              Cc // heads, t_valid, t_pad, float(scale),
                              ptr(out), stream_ptr(q.device))
     check(rc, 'fd_cross_attn')
+    count_launch()
+    return out
+
+
+# --------------------------------------------------------------------------- K5 / K6
+_gn_workspaces = {}
+
+
+def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                  groups: int, eps: float, silu: bool,
+                  bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    '''fd_groupnorm_act on a channels-last bf16 [N,C,H,W] tensor -> same layout.'''
+    if x.dtype != torch.bfloat16 or not x.is_cuda:
+        raise NativeError('groupnorm_act needs a CUDA bfloat16 tensor '
+                          f'(got {x.dtype} on {x.device}); no fallback')
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    N, Cc, H, W = x.shape
+    if bias is not None:
+        _need(bias, 'bias', torch.bfloat16)
+        if tuple(bias.shape) != (N, Cc):
+            raise NativeError(f'bias must be [{N},{Cc}]')
+    y = torch.empty_like(x)  # preserves channels_last
+    key = (x.device, N, groups)
+    ws = _gn_workspaces.get(key)
+    if ws is None:
+        nbytes = lib().fd_groupnorm_act_workspace_bytes(N, groups)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _gn_workspaces[key] = ws
+    rc = lib().fd_groupnorm_act(ptr(x), ptr(bias), ptr(gamma), ptr(beta), ptr(ws),
+                                ptr(y), N, H * W, Cc, groups, float(eps),
+                                int(silu), stream_ptr(x.device))
+    check(rc, 'fd_groupnorm_act')
+    count_launch(2)
+    return y
+
+
+def geglu(x: torch.Tensor) -> torch.Tensor:
+    '''fd_geglu: [..., 2F] bf16 -> [..., F].'''
+    _need(x, 'x', torch.bfloat16)
+    F2 = x.shape[-1]
+    out = torch.empty(x.shape[:-1] + (F2 // 2,), dtype=x.dtype, device=x.device)
+    rc = lib().fd_geglu(ptr(x), ptr(out), x.numel() // F2, F2 // 2,
+                        stream_ptr(x.device))
+    check(rc, 'fd_geglu')
     count_launch()
     return out

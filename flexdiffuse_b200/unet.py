@@ -65,6 +65,12 @@ def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 
 
+def _gn(x: torch.Tensor, norm: nn.GroupNorm, silu: bool, bias=None) -> torch.Tensor:
+    '''GroupNorm (+ optional pre-bias, + optional SiLU) through K5 (`fd_groupnorm_act`).'''
+    return _native.groupnorm_act(x, norm.weight, norm.bias, norm.num_groups, norm.eps,
+                                 silu, bias)
+
+
 class ResnetBlock2D(nn.Module):
     def __init__(self, cin: int, cout: int, temb: int, groups: int):
         super().__init__()
@@ -76,9 +82,10 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb_act):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = h + self.time_emb_proj(temb_act)[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        # K5: GroupNorm + SiLU in one NHWC pass; the time-embedding add is folded into norm2
+        h = self.conv1(_gn(x, self.norm1, silu=True))
+        h = self.conv2(_gn(h, self.norm2, silu=True,
+                           bias=self.time_emb_proj(temb_act)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -134,8 +141,7 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim, inner * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
-        return x * F.gelu(gate)
+        return _native.geglu(self.proj(x))  # K6: x * gelu(gate) in one pass
 
 
 class FeedForward(nn.Module):
@@ -177,7 +183,7 @@ class SpatialTransformer(nn.Module):
 
     def forward(self, x, kv, ctx_index):
         B, C, H, W = x.shape
-        h = self.proj_in(self.norm(x))
+        h = self.proj_in(_gn(x, self.norm, silu=False))
         h = h.permute(0, 2, 3, 1).reshape(B, H * W, C)
         for blk in self.transformer_blocks:
             h = blk(h, kv, ctx_index)
@@ -393,7 +399,7 @@ class UNet2DConditionModel(nn.Module):
         x = self.mid_block(x, emb, kv_cache, ctx_index)
         for blk in self.up_blocks:
             x = blk(x, skips, emb, kv_cache, ctx_index)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        x = self.conv_out(_gn(x, self.conv_norm_out, silu=True))
         return UNetOutput(sample=x)
 
 

@@ -175,6 +175,30 @@ int fd_cross_attn(const void* q_bf16_dev,
                   void* out_bf16_dev,
                   void* stream);
 
+/* ---- K5 / K6: normalisation + activation glue of the UNet forward --------------------- *
+ * The UNet call at pipeline/guide.py:56-58 spends ~45 % of a B=1 denoising step in ATen's
+ * GroupNorm path (layout copy, moments, params, apply, separate SiLU, separate time-embedding
+ * add) and the GEGLU gelu/mul pair (profiles/r01/SUMMARY.md).  Fused, NHWC, bf16:
+ *   y = act( GroupNorm(x + bias[n,c]) * gamma[c] + beta[c] ),  act = SiLU or identity
+ * replaces diffusers ResnetBlock2D's  norm1 -> SiLU  and  (+ time_emb_proj) -> norm2 -> SiLU,
+ * SpatialTransformer.norm and conv_norm_out -> SiLU.                                       */
+int fd_groupnorm_act_workspace_bytes(int N, int G);   /* size of `workspace_dev`            */
+
+int fd_groupnorm_act(const void* x_bf16_dev,     /* [N, HW, C] channels-last activations    */
+                     const void* bias_bf16_dev,  /* [N, C] added before the norm, or NULL   */
+                     const void* gamma_bf16_dev, /* [C]                                     */
+                     const void* beta_bf16_dev,  /* [C]                                     */
+                     void*       workspace_dev,  /* fd_groupnorm_act_workspace_bytes(N, G)  */
+                     void*       y_bf16_dev,     /* [N, HW, C]                              */
+                     int N, int HW, int C, int G,/* G <= 32, C/G even                       */
+                     float eps, int act_silu, void* stream);
+
+/* diffusers GEGLU: out[m, f] = in[m, f] * gelu(in[m, F + f]), exact (erf) GELU.           */
+int fd_geglu(const void* in_bf16_dev,            /* [M, 2F]                                 */
+             void*       out_bf16_dev,           /* [M, F]                                  */
+             int64_t M, int F,                   /* F % 8 == 0                              */
+             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

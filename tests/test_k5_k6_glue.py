@@ -1,0 +1,54 @@
+'''K5 (fused NHWC GroupNorm + time-embedding bias + SiLU) and K6 (GEGLU) vs plain fp32
+PyTorch on the same bf16-rounded inputs.  Stated tolerance: bf16 output rounding,
+1e-2 relative / 1e-2 absolute on O(1) values.'''
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize('N,C,H,W', [(2, 320, 64, 64), (2, 960, 32, 32),
+                                     (4, 1280, 8, 8), (1, 2560, 16, 16),
+                                     (3, 640, 5, 7), (2, 1920, 32, 32)])
+@pytest.mark.parametrize('silu,with_bias', [(True, False), (True, True),
+                                            (False, False)])
+def test_groupnorm_act_matches_torch(native, cuda_dev, N, C, H, W, silu, with_bias):
+    g = torch.Generator(device=cuda_dev).manual_seed(C + H)
+    x = (torch.randn(N, C, H, W, device=cuda_dev, generator=g) * 1.7 + 0.4)
+    x = x.bfloat16().contiguous(memory_format=torch.channels_last)
+    gamma = (torch.randn(C, device=cuda_dev, generator=g) * 0.3 + 1).bfloat16()
+    beta = (torch.randn(C, device=cuda_dev, generator=g) * 0.2).bfloat16()
+    bias = (torch.randn(N, C, device=cuda_dev, generator=g) * 0.5).bfloat16() \
+        if with_bias else None
+    y = native.groupnorm_act(x, gamma, beta, 32, 1e-5, silu, bias)
+    torch.cuda.synchronize()
+    assert y.is_contiguous(memory_format=torch.channels_last) and y.shape == x.shape
+    xf = x.float()
+    if bias is not None:
+        xf = xf + bias.float()[:, :, None, None]
+    ref = F.group_norm(xf, 32, gamma.float(), beta.float(), 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_groupnorm_accepts_nchw_input_and_rejects_fp32(native, cuda_dev):
+    x = torch.randn(1, 320, 8, 8, device=cuda_dev).bfloat16()  # NCHW strides
+    w = torch.ones(320, device=cuda_dev).bfloat16()
+    b = torch.zeros(320, device=cuda_dev).bfloat16()
+    y = native.groupnorm_act(x, w, b, 32, 1e-6, False)
+    ref = F.group_norm(x.float(), 32, w.float(), b.float(), 1e-6)
+    torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2)
+    with pytest.raises(native.NativeError):
+        native.groupnorm_act(x.float(), w, b, 32, 1e-6, False)
+
+
+@pytest.mark.parametrize('M,Fdim', [(2 * 4096, 1280), (2 * 64, 5120), (77, 2560)])
+def test_geglu_matches_torch(native, cuda_dev, M, Fdim):
+    g = torch.Generator(device=cuda_dev).manual_seed(M)
+    x = (torch.randn(M, 2 * Fdim, device=cuda_dev, generator=g) * 2).bfloat16()
+    out = native.geglu(x)
+    torch.cuda.synchronize()
+    a, gate = x.float().chunk(2, dim=-1)
+    torch.testing.assert_close(out.float(), a * F.gelu(gate), rtol=1e-2, atol=1e-2)
