@@ -25,7 +25,8 @@ FD_BLEND_ZERO_DIVISION = 1
 ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
                'fd_kv_project', 'fd_cross_attn',
-               'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act', 'fd_geglu')
+               'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
+               'fd_add_bias_residual', 'fd_geglu')
 
 
 class NativeError(RuntimeError):
@@ -92,8 +93,10 @@ def lib() -> C.CDLL:
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp
     ]
     l.fd_cross_attn.restype = C.c_int
-    l.fd_groupnorm_act_workspace_bytes.argtypes = [C.c_int, C.c_int]
-    l.fd_groupnorm_act_workspace_bytes.restype = C.c_int
+    l.fd_groupnorm_act_workspace_bytes.argtypes = [C.c_int] * 4
+    l.fd_groupnorm_act_workspace_bytes.restype = C.c_int64
+    l.fd_add_bias_residual.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp]
+    l.fd_add_bias_residual.restype = C.c_int
     l.fd_groupnorm_act.argtypes = [
         vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
         C.c_int, vp
@@ -287,6 +290,7 @@ def cross_attn(q: torch.Tensor, kv: torch.Tensor, k_col_off: int,
 
 # --------------------------------------------------------------------------- K5 / K6
 _gn_workspaces = {}
+_gn_retired = []
 
 
 def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
@@ -304,17 +308,19 @@ def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
         if tuple(bias.shape) != (N, Cc):
             raise NativeError(f'bias must be [{N},{Cc}]')
     y = torch.empty_like(x)  # preserves channels_last
-    key = (x.device, N, groups)
-    ws = _gn_workspaces.get(key)
-    if ws is None:
-        nbytes = lib().fd_groupnorm_act_workspace_bytes(N, groups)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        _gn_workspaces[key] = ws
+    nbytes = lib().fd_groupnorm_act_workspace_bytes(N, H * W, Cc, groups)
+    ws = _gn_workspaces.get(x.device)
+    if ws is None or ws.numel() < nbytes:
+        # one grow-only scratch per device; launches on a stream are ordered, so reuse is safe
+        if ws is not None:
+            _gn_retired.append(ws)  # a captured CUDA graph may still point at it
+        ws = torch.empty(max(2 * nbytes, 1 << 24), dtype=torch.uint8, device=x.device)
+        _gn_workspaces[x.device] = ws
     rc = lib().fd_groupnorm_act(ptr(x), ptr(bias), ptr(gamma), ptr(beta), ptr(ws),
                                 ptr(y), N, H * W, Cc, groups, float(eps),
                                 int(silu), stream_ptr(x.device))
     check(rc, 'fd_groupnorm_act')
-    count_launch(2)
+    count_launch(3)
     return y
 
 
@@ -328,3 +334,22 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
     check(rc, 'fd_geglu')
     count_launch()
     return out
+
+
+def add_bias_residual(x: torch.Tensor, h: torch.Tensor,
+                      bias: torch.Tensor) -> torch.Tensor:
+    '''fd_add_bias_residual: x + h + bias[c] on channels-last bf16 [N,C,H,W] tensors.'''
+    for name, t in (('x', x), ('h', h)):
+        if t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise NativeError(f'{name} must be CUDA bfloat16; no fallback')
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    if not h.is_contiguous(memory_format=torch.channels_last):
+        h = h.contiguous(memory_format=torch.channels_last)
+    _need(bias, 'bias', torch.bfloat16)
+    y = torch.empty_like(x)
+    rc = lib().fd_add_bias_residual(ptr(x), ptr(h), ptr(bias), ptr(y), x.numel(),
+                                    x.shape[1], stream_ptr(x.device))
+    check(rc, 'fd_add_bias_residual')
+    count_launch()
+    return y

@@ -9,7 +9,10 @@
 //   K5  y = act( GroupNorm( x + bias[n,c] ) * gamma[c] + beta[c] )        NHWC bf16 in / out
 //       diffusers ResnetBlock2D: norm1 -> SiLU, (+ time_emb_proj) -> norm2 -> SiLU;
 //       SpatialTransformer.norm, conv_norm_out.  Two launches: per-slab partial (sum, sumsq) per
-//       group, then normalise + affine + SiLU.  No atomics, deterministic.
+//       channel pair, a tiny per-group finalise, then normalise + affine + SiLU: three launches, no
+//       atomics, fixed summation order (bit-reproducible).
+//   K7  y = x + h + bias[c]: the resnet residual add with conv2's bias folded in (cuDNN would
+//       otherwise add every convolution bias with a separate broadcast kernel).
 //   K6  out[m, f] = in[m, f] * gelu(in[m, F + f])                          diffusers GEGLU
 #include <math.h>
 
@@ -18,18 +21,20 @@
 namespace fd {
 namespace {
 
-constexpr int GN_THREADS = 256;
+constexpr int GN_THREADS = 256;   // 8 warps: warp w takes rows w, w+8, ... of the slab
+constexpr int GN_WARPS = GN_THREADS / 32;
+constexpr int GN_ROWS = 32;        // rows (pixels) per CTA
 constexpr int GN_MAX_GROUPS = 32;
-constexpr int GN_MAX_SLABS = 64;
 
 struct GnArgs {
   const __nv_bfloat16* x;      // [N, HW, C] (channels_last view of [N, C, H, W])
   const __nv_bfloat16* bias;   // [N, C] or nullptr
   const __nv_bfloat16* gamma;  // [C]
   const __nv_bfloat16* beta;   // [C]
-  float* partial;              // [N, slabs, G, 2]
+  float2* partial;             // [N, slabs, C/2]  per channel-pair (sum, sumsq) of one slab
+  float2* stats;               // [N, G]           (mean, rstd)
   __nv_bfloat16* y;            // [N, HW, C]
-  int HW, C, G, slabs, rows_per_slab;
+  int HW, C, G, slabs;
   float eps;
   int act_silu;
 };
@@ -38,104 +43,137 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
 }
 
-// phase 1: partial sums.  grid (slabs, N).  Thread t owns channel pairs t, t+256, ... (coalesced
-// across the warp); a channel pair never straddles a group because C/G is even.
+// phase 1.  grid (C/64, slabs, N): one CTA = 32 channel pairs x 32 rows; a warp reads 128
+// contiguous bytes per row, 4 rows in flight per thread.  Fixed reduction order (no atomics).
 __global__ void __launch_bounds__(GN_THREADS) k5_gn_stats_kernel(const GnArgs a) {
-  __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
-  const int n = blockIdx.y, slab = blockIdx.x;
+  __shared__ float2 red[GN_WARPS][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pairs = a.C >> 1;
-  const int cg2 = (a.C / a.G) >> 1;  // channel pairs per group
-  if (threadIdx.x < GN_MAX_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
+  const int p = blockIdx.x * 32 + lane;
+  const int slab = blockIdx.y, n = blockIdx.z;
+  const int r0 = slab * GN_ROWS;
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + static_cast<size_t>(n) * a.HW * pairs + p;
+  float2 b = make_float2(0.f, 0.f);
+  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias)[static_cast<size_t>(n) * pairs + p]);
+  uint32_t v[GN_ROWS / GN_WARPS];
+#pragma unroll
+  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
+    const int r = r0 + warp + i * GN_WARPS;
+    v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
   }
-  __syncthreads();
-  const int r0 = slab * a.rows_per_slab;
-  const int r1 = min(a.HW, r0 + a.rows_per_slab);
-  const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + static_cast<size_t>(n) * a.HW * pairs;
-  const uint32_t* bb = a.bias ? reinterpret_cast<const uint32_t*>(a.bias) + static_cast<size_t>(n) * pairs : nullptr;
-  for (int p = threadIdx.x; p < pairs; p += GN_THREADS) {
-    float2 b = bb ? bf2_to_f2(bb[p]) : make_float2(0.f, 0.f);
-    float s = 0.f, q = 0.f;
-    int r = r0;
-    for (; r + 4 <= r1; r += 4) {
-      uint32_t v0 = xb[static_cast<size_t>(r) * pairs + p];
-      uint32_t v1 = xb[static_cast<size_t>(r + 1) * pairs + p];
-      uint32_t v2 = xb[static_cast<size_t>(r + 2) * pairs + p];
-      uint32_t v3 = xb[static_cast<size_t>(r + 3) * pairs + p];
-      float2 f0 = bf2_to_f2(v0), f1 = bf2_to_f2(v1), f2 = bf2_to_f2(v2), f3 = bf2_to_f2(v3);
-      f0.x += b.x; f0.y += b.y; f1.x += b.x; f1.y += b.y;
-      f2.x += b.x; f2.y += b.y; f3.x += b.x; f3.y += b.y;
-      s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-      q += (f0.x * f0.x + f0.y * f0.y) + (f1.x * f1.x + f1.y * f1.y) + (f2.x * f2.x + f2.y * f2.y) +
-           (f3.x * f3.x + f3.y * f3.y);
-    }
-    for (; r < r1; ++r) {
-      float2 f = bf2_to_f2(xb[static_cast<size_t>(r) * pairs + p]);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
+    const int r = r0 + warp + i * GN_WARPS;
+    if (r < a.HW) {
+      float2 f = bf2_to_f2(v[i]);
       f.x += b.x;
       f.y += b.y;
       s += f.x + f.y;
       q += f.x * f.x + f.y * f.y;
     }
-    const int g = p / cg2;
-    atomicAdd(&s_sum[g], s);
-    atomicAdd(&s_sq[g], q);
   }
+  red[warp][lane] = make_float2(s, q);
   __syncthreads();
-  if (threadIdx.x < a.G) {
-    float* dst = a.partial + ((static_cast<size_t>(n) * a.slabs + slab) * a.G + threadIdx.x) * 2;
-    dst[0] = s_sum[threadIdx.x];
-    dst[1] = s_sq[threadIdx.x];
+  if (warp == 0) {
+    float2 t = red[0][lane];
+#pragma unroll
+    for (int w = 1; w < GN_WARPS; ++w) {
+      t.x += red[w][lane].x;
+      t.y += red[w][lane].y;
+    }
+    a.partial[(static_cast<size_t>(n) * a.slabs + slab) * pairs + p] = t;
   }
 }
 
-// phase 2: normalise + affine + optional SiLU.  Same grid / mapping.
-__global__ void __launch_bounds__(GN_THREADS) k5_gn_apply_kernel(const GnArgs a) {
-  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  const int n = blockIdx.y, slab = blockIdx.x;
-  const int pairs = a.C >> 1;
-  const int cg = a.C / a.G, cg2 = cg >> 1;
-  if (threadIdx.x < a.G) {
-    float s = 0.f, q = 0.f;
-    const float* src = a.partial + (static_cast<size_t>(n) * a.slabs * a.G + threadIdx.x) * 2;
-    for (int k = 0; k < a.slabs; ++k) {
-      s += src[static_cast<size_t>(k) * a.G * 2];
-      q += src[static_cast<size_t>(k) * a.G * 2 + 1];
-    }
-    const float cnt = static_cast<float>(a.HW) * cg;
-    const float mean = s / cnt;
-    const float var = fmaxf(q / cnt - mean * mean, 0.f);
-    s_mean[threadIdx.x] = mean;
-    s_rstd[threadIdx.x] = rsqrtf(var + a.eps);
+// phase 2.  grid (G, N): reduce the partials of one group to (mean, rstd), fixed order.
+__global__ void __launch_bounds__(256) k5_gn_finalize_kernel(const GnArgs a) {
+  __shared__ float2 red[256];
+  const int g = blockIdx.x, n = blockIdx.y;
+  const int pairs = a.C >> 1, cg2 = (a.C / a.G) >> 1;
+  const int total = a.slabs * cg2;
+  float s = 0.f, q = 0.f;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int slab = i / cg2, k = i - slab * cg2;
+    const float2 t = a.partial[(static_cast<size_t>(n) * a.slabs + slab) * pairs + g * cg2 + k];
+    s += t.x;
+    q += t.y;
   }
+  red[threadIdx.x] = make_float2(s, q);
   __syncthreads();
-  const int r0 = slab * a.rows_per_slab;
-  const int r1 = min(a.HW, r0 + a.rows_per_slab);
-  const size_t base = static_cast<size_t>(n) * a.HW * pairs;
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      red[threadIdx.x].x += red[threadIdx.x + o].x;
+      red[threadIdx.x].y += red[threadIdx.x + o].y;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
+    const float mean = red[0].x / cnt;
+    const float var = fmaxf(red[0].y / cnt - mean * mean, 0.f);
+    a.stats[static_cast<size_t>(n) * a.G + g] = make_float2(mean, rsqrtf(var + a.eps));
+  }
+}
+
+// phase 3: normalise + affine + optional SiLU, same tiling as phase 1.
+__global__ void __launch_bounds__(GN_THREADS) k5_gn_apply_kernel(const GnArgs a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int pairs = a.C >> 1, cg2 = (a.C / a.G) >> 1;
+  const int p = blockIdx.x * 32 + lane;
+  const int slab = blockIdx.y, n = blockIdx.z;
+  const int r0 = slab * GN_ROWS;
+  const size_t base = static_cast<size_t>(n) * a.HW * pairs + p;
   const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + base;
   uint32_t* yb = reinterpret_cast<uint32_t*>(a.y) + base;
-  const uint32_t* bb = a.bias ? reinterpret_cast<const uint32_t*>(a.bias) + static_cast<size_t>(n) * pairs : nullptr;
-  const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.gamma);
-  const uint32_t* tb = reinterpret_cast<const uint32_t*>(a.beta);
-  for (int p = threadIdx.x; p < pairs; p += GN_THREADS) {
-    const int g = p / cg2;
-    const float mean = s_mean[g], rstd = s_rstd[g];
-    const float2 gam = bf2_to_f2(gb[p]), bet = bf2_to_f2(tb[p]);
-    const float2 b = bb ? bf2_to_f2(bb[p]) : make_float2(0.f, 0.f);
-    // y = (x + b - mean) * rstd * gamma + beta  =  x * sc + sh
-    const float scx = rstd * gam.x, scy = rstd * gam.y;
-    const float shx = (b.x - mean) * scx + bet.x, shy = (b.y - mean) * scy + bet.y;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) {
-      const float2 f = bf2_to_f2(xb[static_cast<size_t>(r) * pairs + p]);
+  uint32_t v[GN_ROWS / GN_WARPS];
+#pragma unroll
+  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
+    const int r = r0 + warp + i * GN_WARPS;
+    v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
+  }
+  const float2 st = a.stats[static_cast<size_t>(n) * a.G + p / cg2];
+  const float2 gam = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.gamma)[p]);
+  const float2 bet = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.beta)[p]);
+  float2 b = make_float2(0.f, 0.f);
+  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias)[static_cast<size_t>(n) * pairs + p]);
+  // y = (x + b - mean) * rstd * gamma + beta  =  x * sc + sh
+  const float scx = st.y * gam.x, scy = st.y * gam.y;
+  const float shx = (b.x - st.x) * scx + bet.x, shy = (b.y - st.x) * scy + bet.y;
+#pragma unroll
+  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
+    const int r = r0 + warp + i * GN_WARPS;
+    if (r < a.HW) {
+      const float2 f = bf2_to_f2(v[i]);
       float ox = f.x * scx + shx, oy = f.y * scy + shy;
       if (a.act_silu) {
         ox = ox / (1.0f + __expf(-ox));
         oy = oy / (1.0f + __expf(-oy));
       }
       __nv_bfloat162 o = __floats2bfloat162_rn(ox, oy);
-      yb[static_cast<size_t>(r) * pairs + p] = *reinterpret_cast<uint32_t*>(&o);
+      yb[static_cast<size_t>(r) * pairs] = *reinterpret_cast<uint32_t*>(&o);
     }
+  }
+}
+
+// K7: y = x + h + bias[c]   (residual add with the convolution bias folded in), NHWC bf16
+__global__ void __launch_bounds__(256) k7_add_bias_residual_kernel(const uint4* __restrict__ x,
+                                                                   const uint4* __restrict__ h,
+                                                                   const uint4* __restrict__ bias, uint4* __restrict__ y,
+                                                                   int64_t total8, int c8) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 xv = x[i], hv = h[i], bv = bias[i % c8];
+    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w}, hs[4] = {hv.x, hv.y, hv.z, hv.w},
+                   bs[4] = {bv.x, bv.y, bv.z, bv.w};
+    uint32_t os[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 a = bf2_to_f2(xs[k]), b = bf2_to_f2(hs[k]), c = bf2_to_f2(bs[k]);
+      __nv_bfloat162 o = __floats2bfloat162_rn(a.x + (b.x + c.x), a.y + (b.y + c.y));
+      os[k] = *reinterpret_cast<uint32_t*>(&o);
+    }
+    y[i] = make_uint4(os[0], os[1], os[2], os[3]);
   }
 }
 
@@ -169,8 +207,9 @@ __global__ void __launch_bounds__(256) k6_geglu_kernel(const __nv_bfloat16* __re
 }  // namespace
 }  // namespace fd
 
-extern "C" int fd_groupnorm_act_workspace_bytes(int N, int G) {
-  return N * fd::GN_MAX_SLABS * G * 2 * static_cast<int>(sizeof(float));
+extern "C" int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G) {
+  const int64_t slabs = (HW + fd::GN_ROWS - 1) / fd::GN_ROWS;
+  return (static_cast<int64_t>(N) * slabs * (C / 2) + static_cast<int64_t>(N) * G) * 8;
 }
 
 extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
@@ -180,37 +219,56 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && workspace_dev && y_bf16_dev,
              "fd_groupnorm_act: NULL pointer");
   FD_REQUIRE(N > 0 && HW > 0 && C > 0, "fd_groupnorm_act: non-positive shape");
-  FD_REQUIRE(G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 2 == 0,
-             "fd_groupnorm_act: need G <= %d, C %% G == 0 and an even number of channels per group (C=%d G=%d)",
+  FD_REQUIRE(G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 2 == 0 && C % 64 == 0,
+             "fd_groupnorm_act: need G <= %d, C %% G == 0, even channels per group, C %% 64 == 0 (C=%d G=%d)",
              GN_MAX_GROUPS, C, G);
-  FD_REQUIRE(N <= 65535, "fd_groupnorm_act: N exceeds grid limits");
+  const int slabs = (HW + GN_ROWS - 1) / GN_ROWS;
+  FD_REQUIRE(N <= 65535 && slabs <= 65535, "fd_groupnorm_act: shape exceeds grid limits");
+  FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 8 == 0, "fd_groupnorm_act: workspace must be 8-byte aligned");
   int rc = check_device();
   if (rc != FD_OK) return rc;
-  const int sms = sm_count();
-  if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_groupnorm_act: cannot query SM count");
   GnArgs a;
   a.x = static_cast<const __nv_bfloat16*>(x_bf16_dev);
   a.bias = static_cast<const __nv_bfloat16*>(bias_bf16_dev);
   a.gamma = static_cast<const __nv_bfloat16*>(gamma_bf16_dev);
   a.beta = static_cast<const __nv_bfloat16*>(beta_bf16_dev);
-  a.partial = static_cast<float*>(workspace_dev);
+  a.partial = static_cast<float2*>(workspace_dev);
+  a.stats = a.partial + static_cast<size_t>(N) * slabs * (C / 2);
   a.y = static_cast<__nv_bfloat16*>(y_bf16_dev);
   a.HW = HW;
   a.C = C;
   a.G = G;
+  a.slabs = slabs;
   a.eps = eps;
   a.act_silu = act_silu;
-  // about two CTAs per SM over the whole batch, at least 8 rows per slab
-  int slabs = (2 * sms + N - 1) / N;
-  if (slabs > GN_MAX_SLABS) slabs = GN_MAX_SLABS;
-  if (slabs > (HW + 7) / 8) slabs = (HW + 7) / 8;
-  if (slabs < 1) slabs = 1;
-  a.rows_per_slab = (HW + slabs - 1) / slabs;
-  a.slabs = (HW + a.rows_per_slab - 1) / a.rows_per_slab;
-  dim3 grid(a.slabs, N);
+  dim3 grid(C / 64, slabs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   k5_gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(a);
+  k5_gn_finalize_kernel<<<dim3(G, N), 256, 0, st>>>(a);
   k5_gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(a);
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
+}
+
+extern "C" int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev, const void* bias_bf16_dev,
+                                    void* y_bf16_dev, int64_t n_elem, int C, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(x_bf16_dev && h_bf16_dev && bias_bf16_dev && y_bf16_dev, "fd_add_bias_residual: NULL pointer");
+  FD_REQUIRE(C > 0 && C % 8 == 0 && n_elem > 0 && n_elem % C == 0,
+             "fd_add_bias_residual: need C %% 8 == 0 and n_elem a multiple of C");
+  auto mis = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 != 0; };
+  FD_REQUIRE(!mis(x_bf16_dev) && !mis(h_bf16_dev) && !mis(bias_bf16_dev) && !mis(y_bf16_dev),
+             "fd_add_bias_residual: pointers must be 16-byte aligned");
+  int rc = check_device();
+  if (rc != FD_OK) return rc;
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_add_bias_residual: cannot query SM count");
+  const int64_t total8 = n_elem / 8;
+  int64_t want = (total8 + 255) / 256, cap = static_cast<int64_t>(sms) * 8;
+  k7_add_bias_residual_kernel<<<static_cast<unsigned>(want < cap ? want : cap), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x_bf16_dev), static_cast<const uint4*>(h_bf16_dev),
+      static_cast<const uint4*>(bias_bf16_dev), static_cast<uint4*>(y_bf16_dev), total8, C / 8);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

@@ -182,16 +182,21 @@ int fd_cross_attn(const void* q_bf16_dev,
  *   y = act( GroupNorm(x + bias[n,c]) * gamma[c] + beta[c] ),  act = SiLU or identity
  * replaces diffusers ResnetBlock2D's  norm1 -> SiLU  and  (+ time_emb_proj) -> norm2 -> SiLU,
  * SpatialTransformer.norm and conv_norm_out -> SiLU.                                       */
-int fd_groupnorm_act_workspace_bytes(int N, int G);   /* size of `workspace_dev`            */
+int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G); /* size of `workspace_dev` */
 
 int fd_groupnorm_act(const void* x_bf16_dev,     /* [N, HW, C] channels-last activations    */
                      const void* bias_bf16_dev,  /* [N, C] added before the norm, or NULL   */
                      const void* gamma_bf16_dev, /* [C]                                     */
                      const void* beta_bf16_dev,  /* [C]                                     */
-                     void*       workspace_dev,  /* fd_groupnorm_act_workspace_bytes(N, G)  */
+                     void*       workspace_dev,  /* fd_groupnorm_act_workspace_bytes(...)   */
                      void*       y_bf16_dev,     /* [N, HW, C]                              */
-                     int N, int HW, int C, int G,/* G <= 32, C/G even                       */
+                     int N, int HW, int C, int G,/* G <= 32, C/G even, C % 64 == 0          */
                      float eps, int act_silu, void* stream);
+
+/* y = x + h + bias[c]: ResnetBlock2D's residual add with conv2's bias folded in (NHWC bf16). */
+int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev,
+                         const void* bias_bf16_dev,  /* [C]                                 */
+                         void* y_bf16_dev, int64_t n_elem, int C, void* stream);
 
 /* diffusers GEGLU: out[m, f] = in[m, f] * gelu(in[m, F + f]), exact (erf) GELU.           */
 int fd_geglu(const void* in_bf16_dev,            /* [M, 2F]                                 */

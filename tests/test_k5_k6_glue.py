@@ -52,3 +52,26 @@ def test_geglu_matches_torch(native, cuda_dev, M, Fdim):
     torch.cuda.synchronize()
     a, gate = x.float().chunk(2, dim=-1)
     torch.testing.assert_close(out.float(), a * F.gelu(gate), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('N,C,H,W', [(2, 320, 64, 64), (4, 1280, 8, 8)])
+def test_add_bias_residual_matches_torch(native, cuda_dev, N, C, H, W):
+    g = torch.Generator(device=cuda_dev).manual_seed(C)
+    mk = lambda: torch.randn(N, C, H, W, device=cuda_dev, generator=g).bfloat16() \
+        .contiguous(memory_format=torch.channels_last)
+    x, h = mk(), mk()
+    b = torch.randn(C, device=cuda_dev, generator=g).bfloat16()
+    y = native.add_bias_residual(x, h, b)
+    ref = x.float() + (h.float() + b.float()[None, :, None, None])
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2)
+
+
+def test_groupnorm_is_bit_reproducible(native, cuda_dev):
+    x = torch.randn(2, 640, 32, 32, device=cuda_dev).bfloat16() \
+        .contiguous(memory_format=torch.channels_last)
+    w = torch.randn(640, device=cuda_dev).bfloat16()
+    b = torch.randn(640, device=cuda_dev).bfloat16()
+    a = native.groupnorm_act(x, w, b, 32, 1e-5, True)
+    for _ in range(3):
+        assert torch.equal(a, native.groupnorm_act(x, w, b, 32, 1e-5, True))
