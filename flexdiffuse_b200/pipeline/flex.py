@@ -122,8 +122,10 @@ class FlexPipeline():
                  generator: Optional[torch.Generator] = None,
                  output_type: str = 'pil',
                  return_dict: bool = True,
-                 debug: bool = False):
-        '''Arguments as flex.py:127-168.  `output_type='latent'` additionally returns the
+                 debug: bool = False,
+                 latents: Optional[torch.Tensor] = None):
+        '''Arguments as flex.py:127-168, plus `latents`: pre-drawn initial noise [B,4,h,w]
+        (txt2img only; used by the sweep driver for shard-invariant per-sample seeds).  `output_type='latent'` additionally returns the
         final latents without decoding (sweep driver) and `'pt'` the decoded images as a
         device tensor.'''
         if strength < 0 or strength > 1:
@@ -161,7 +163,11 @@ class FlexPipeline():
         else:
             height, width = init_size
             shape = (batch_size, self.unet.in_channels, height // 8, width // 8)
-            if generator is not None and generator.device.type == 'cpu':
+            if latents is not None:
+                if tuple(latents.shape) != shape:
+                    raise ValueError(f'latents must be {shape}, got {tuple(latents.shape)}')
+                init_latents = latents.to(self.device, torch.float32)
+            elif generator is not None and generator.device.type == 'cpu':
                 # host-side RNG (reproducible across devices): draw on the host, copy once
                 init_latents = torch.randn(shape, generator=generator).pin_memory().to(
                     self.device, non_blocking=True)

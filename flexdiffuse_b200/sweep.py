@@ -58,3 +58,27 @@ def run_sweep(n_samples: int,
     dist.all_gather_into_tensor(buf, pad)
     parts = [buf[r * width:r * width + (h - l)] for r, (l, h) in enumerate(counts)]
     return torch.cat(parts)
+
+
+def make_denoiser(pipe, encoder, unet, contexts: torch.Tensor, seeds: Sequence[int],
+                  guidance: float, steps: int, init_size=(512, 512),
+                  use_cuda_graph: bool = True) -> Callable[[int, int], torch.Tensor]:
+    '''denoise(lo, hi) for `run_sweep`: sample i uses context `contexts[i]` ([N,77,768], e.g. the
+    K1 blends of a prompt x guidance-parameter grid) and noise seeded `seeds[i]`.'''
+    from .pipeline.guide import SimpleGuide
+    h, w = init_size
+    dev = contexts.device
+
+    def denoise(lo: int, hi: int) -> torch.Tensor:
+        if hi <= lo:
+            return torch.zeros((0, unet.in_channels, h // 8, w // 8), device=dev)
+        guide = SimpleGuide(encoder, unet, guidance, steps, contexts[lo:hi],
+                            use_cuda_graph=use_cuda_graph)
+        noise = torch.stack([
+            sample_noise(seeds[i], (unet.in_channels, h // 8, w // 8), dev)
+            for i in range(lo, hi)
+        ])
+        return pipe(guide, init_size=init_size, latents=noise, output_type='latent',
+                    return_dict=False)
+
+    return denoise

@@ -1,0 +1,127 @@
+'''BASELINE.json configs[2..4] as parity cases (GPU), scaled down in resolution / steps so the
+fp32 oracle finishes in seconds; the full-size runs are bench lines, not tests.
+
+  configs[2]: image guidance (all three modes) blended into the 77-token context, batch 8,
+              cached cross-attention K/V                         -> K1 + K2 + K3 + K4
+  configs[3]: img2img strength 0.6 + image guidance, PNDM, batch 16, bf16
+  configs[4]: guidance-parameter x seed sweep sharded over ranks (single process here; the
+              2-rank path is tests/test_sweep_gloo.py)'''
+import numpy as np
+import pytest
+import torch
+
+from flexdiffuse_b200 import guidance as G
+from flexdiffuse_b200 import schedulers as prod
+from flexdiffuse_b200 import sweep
+from flexdiffuse_b200.pipeline.flex import FlexPipeline
+from flexdiffuse_b200.pipeline.guide import SimpleGuide
+from oracle import guidance_oracle as orc
+from oracle import loop_oracle as lo
+from oracle import unet_oracle as U
+from tests.model_helpers import models, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+class _Enc:
+    def __init__(self, uncond):
+        self.uncond = uncond
+
+    def prompt(self, p):
+        return self.uncond
+
+
+def _prompts_and_guide(B, seed):
+    _, img = orc.synthetic_pair(seed, planted=0)
+    txts = []
+    for b in range(B):
+        t, _ = orc.synthetic_pair(seed + 1 + b, planted=0)
+        for k in range(4):  # a few aligned tokens so every weight branch fires
+            img_row = 7 * b + 3 * k + 1
+            t[0, 2 + 3 * k] = img[0, img_row] * (1.0 + 0.1 * k)
+        txts.append(t)
+    return torch.cat(txts), img
+
+
+@pytest.mark.parametrize('mode,reuse', [(1, True), (0, False), (2, True)])
+def test_config2_guided_batch8_cached_kv(native, cuda_dev, mode, reuse):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    unet, vae, usd, _ = models(str(cuda_dev))
+    B, steps, hw = 8, 3, 128
+    txt, img = _prompts_and_guide(B, 31)
+    tw = G.Tweener((0.3, 0.5), (0.1, 0.5), 0.0, 0.35, 0.15, mode, reuse)
+    ctx, res = tw.tween_batch(txt.to(cuda_dev), img.to(cuda_dev))
+    want_ctx = orc.tween_batch(txt, img, orc.TweenParams(
+        threshold=(0.3, 0.5), linear=(0.1, 0.5), clustered=0.0, max_guidance=0.35,
+        align_mode=mode, mapping_reuse=reuse), rowwise=False)
+    assert (ctx.cpu() == want_ctx).all(-1).float().mean() > 0.98
+    assert not torch.equal(ctx.cpu(), txt)  # guidance actually changed the context
+    g = torch.Generator(device=cuda_dev).manual_seed(2)
+    uncond = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    pipe = FlexPipeline(vae, None, None, unet, prod.DDIMScheduler())
+    guide = SimpleGuide(_Enc(uncond), unet, 7.5, steps, ctx)
+    lat = pipe(guide, init_size=(hw, hw),
+               generator=torch.Generator(device=cuda_dev).manual_seed(4),
+               output_type='latent', return_dict=False)
+    assert guide._kv.n_ctx == B + 1  # uncond row shared by the whole batch (Q17)
+    want = lo.denoise(lambda x, t, c: U.unet_forward(usd, x, t, c.bfloat16().float()),
+                      lo.DDIMScheduler(), uncond, ctx, 7.5, steps, init_size=(hw, hw),
+                      generator=torch.Generator(device=cuda_dev).manual_seed(4),
+                      device=cuda_dev)
+    assert rel_l2(lat, want) < 5e-2
+
+
+def test_config3_img2img_pndm_batch16(native, cuda_dev):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    unet, vae, usd, vsd = models(str(cuda_dev))
+    B, steps, hw = 16, 5, 128
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    uncond = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    ctx = torch.randn(B, 77, 768, device=cuda_dev, generator=g)
+    init = torch.rand(1, 3, hw, hw, device=cuda_dev, generator=g) * 2 - 1
+    pipe = FlexPipeline(vae, None, None, unet, prod.PNDMScheduler())
+    guide = SimpleGuide(_Enc(uncond), unet, 7.5, steps, ctx)
+    lat = pipe(guide, init_image=init, strength=0.6,
+               generator=torch.Generator(device=cuda_dev).manual_seed(6),
+               output_type='latent', return_dict=False)
+    gen = torch.Generator(device=cuda_dev).manual_seed(6)
+    # the product VAE encodes in bf16; give the oracle loop the same posterior sample by
+    # drawing it with the same generator state from the fp32 oracle VAE
+    moments = U.vae_encode_moments(vsd, init)
+    mean, logvar = moments.chunk(2, dim=1)
+    std = torch.exp(0.5 * logvar.clamp(-30, 20))
+    init_lat = 0.18215 * (mean + std * torch.randn(mean.shape, generator=gen,
+                                                   device=cuda_dev))
+    want = lo.denoise(lambda x, t, c: U.unet_forward(usd, x, t, c.bfloat16().float()),
+                      lo.PNDMScheduler(), uncond, ctx, 7.5, steps,
+                      init_latents=init_lat, strength=0.6, generator=gen,
+                      device=cuda_dev)
+    assert tuple(lat.shape) == (B, 4, hw // 8, hw // 8)
+    assert rel_l2(lat, want) < 6e-2
+
+
+def test_config4_sweep_is_shard_and_batch_invariant(native, cuda_dev):
+    unet, vae, _, _ = models(str(cuda_dev))
+    n, steps, hw = 12, 2, 128
+    txt, img = _prompts_and_guide(3, 57)
+    rs = np.random.RandomState(0)
+    # grid: 3 prompts x 2 parameter sets x 2 seeds
+    ctxs = []
+    for p in range(2):
+        tw = G.Tweener((0.3, 0.5), (0.0, 0.2 + 0.3 * p), 0.0, 0.35 + 0.1 * p)
+        ctxs.append(tw.tween_batch(txt.to(cuda_dev), img.to(cuda_dev))[0])
+    contexts = torch.cat(ctxs).repeat_interleave(2, dim=0)  # [12,77,768]
+    seeds = [1000 + i for i in range(n)]
+    uncond = torch.randn(1, 77, 768, device=cuda_dev)
+    pipe = FlexPipeline(vae, None, None, unet, prod.DDIMScheduler())
+    den = sweep.make_denoiser(pipe, _Enc(uncond), unet, contexts, seeds, 7.5, steps,
+                              init_size=(hw, hw), use_cuda_graph=False)
+    a = sweep.run_sweep(n, den, micro_batch=4)
+    b = sweep.run_sweep(n, den, micro_batch=6)
+    assert tuple(a.shape) == (n, 4, hw // 8, hw // 8)
+    # same samples, different micro-batching: cuDNN/cuBLAS may pick other tilings => tolerance
+    assert rel_l2(a, b) < 2e-2
+    # different seeds / parameters give different latents
+    assert rel_l2(a[0], a[1]) > 0.1
