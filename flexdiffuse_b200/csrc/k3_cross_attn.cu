@@ -5,41 +5,48 @@
 // for each of the 16 attn2 layers of the SD-v1 UNet.  K and V are column
 // slices of the K2 output, so nothing about the context is recomputed inside the loop.
 //
-// One CTA = one (sample, head, 128-query tile).  4 warps:
-//   thread 0       : TMA loads (Q tile, K, V; SWIZZLE_128B, zero-filled to 64-wide d chunks and
-//                    to 80 keys) and the two tcgen05.mma chains
-//   all 128 threads: one TMEM lane = one query row -> softmax over the 77 keys entirely in
-//                    registers, P written back to TMEM as bf16 (A operand of the second MMA),
-//                    epilogue O / rowsum -> bf16 -> global.
-//   S = Q K^T : M=128, N=80, K=d (k-steps of 16)   both operands K-major in smem
+// v2 (round 1, after the first ncu pass showed v1 latency-bound at <=20 warps/SM with a serial
+// TMA -> MMA -> softmax -> MMA -> store chain per CTA): warp-specialised and software-pipelined.
+// A CTA owns one (sample, head) and walks over several 128-query tiles:
+//   warp 0        : TMA producer -- K and V once, then the Q tiles through a 2-stage ring
+//   warp 1        : tcgen05.mma issuer -- S_i = Q_i K^T is issued while the softmax warps still
+//                   work on tile i-1; O_i = P_i V follows as soon as P_i is in TMEM
+//   warps 2..5    : one TMEM lane = one query row -> softmax over the 77 keys in registers,
+//                   P written back to TMEM as bf16 (A operand of the second MMA); the epilogue
+//                   of tile i-1 (O / rowsum -> bf16 -> global) runs after the softmax of tile i
+//                   so the P V latency is hidden.
+//   S = Q K^T : M=128, N=80, K=d (k-steps of 16)   both operands K-major SWIZZLE_128B in smem
 //   O = P V   : M=128, N=d (rounded to 16), K=80   A = P from TMEM, B = V MN-major in smem
-// TMEM columns: S [0,80) fp32, P [0,40) bf16x2 aliasing S, O [40, 40+N) (S is dead by then).
-// HBM-bound by design (AI = 77 FLOP/B): the point is to read Q once, write O once.
+// TMEM: two buffers; in each  S [0,80) fp32,  P [0,40) bf16x2 aliasing S,  O [40, 40+N)
+// (S is dead once P is written).  HBM-bound by design (AI = 77 FLOP/B).
 #include "fd_common.cuh"
 
 namespace fd {
 namespace {
 
-constexpr int TQ = 128;     // query rows per CTA
+constexpr int TQ = 128;     // query rows per tile
 constexpr int TKV = 80;     // keys padded 77 -> 80
-constexpr int K3_THREADS = 128;
+constexpr int K3_THREADS = 192;
 constexpr int Q_CHUNK_BYTES = TQ * 128;
 constexpr int KV_CHUNK_BYTES = TKV * 128;
 constexpr int O_COL = 40;
+constexpr int QSTAGES = 2;
 
 template <int DH>
 struct K3Cfg {
   static constexpr int NCHUNK = (DH + 63) / 64;        // 64-element d chunks (128 B swizzle rows)
   static constexpr int KSTEPS = (DH + 15) / 16;        // UMMA k-steps for Q K^T
   static constexpr int NPV = ((DH + 15) / 16) * 16;    // UMMA N for P V
-  static constexpr int TMEM_COLS = (O_COL + NPV) <= 128 ? 128 : 256;
-  static constexpr int SMEM = 1024 + NCHUNK * (Q_CHUNK_BYTES + 2 * KV_CHUNK_BYTES) + 64;
+  static constexpr int BUF_COLS = O_COL + NPV;         // TMEM columns per accumulator buffer
+  static constexpr int TMEM_COLS = 2 * BUF_COLS <= 256 ? 256 : 512;
+  static constexpr int Q_STAGE_BYTES = NCHUNK * Q_CHUNK_BYTES;
+  static constexpr int SMEM = 1024 + QSTAGES * Q_STAGE_BYTES + 2 * NCHUNK * KV_CHUNK_BYTES + 256;
 };
 
 struct K3Args {
   const int32_t* ctx_index;
   __nv_bfloat16* out;
-  int n_q, heads, t_valid, t_pad;
+  int n_q, heads, t_valid, t_pad, n_tiles;
   float scale_log2e;
 };
 
@@ -51,34 +58,43 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sq = smem;
-  uint8_t* sk = sq + Cfg::NCHUNK * Q_CHUNK_BYTES;
+  uint8_t* sq = smem;                                   // QSTAGES x [NCHUNK x 128 x 128 B]
+  uint8_t* sk = sq + QSTAGES * Cfg::Q_STAGE_BYTES;      // NCHUNK x 80 x 128 B
   uint8_t* sv = sk + Cfg::NCHUNK * KV_CHUNK_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sv + Cfg::NCHUNK * KV_CHUNK_BYTES);
-  uint64_t* qk_bar = bars;      // Q + K landed
-  uint64_t* v_bar = bars + 1;   // V landed
-  uint64_t* s_bar = bars + 2;   // S = Q K^T complete
-  uint64_t* o_bar = bars + 3;   // O = P V complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* kv_full = bars;          // K + V landed
+  uint64_t* q_full = bars + 1;       // [2] Q stage landed
+  uint64_t* q_empty = bars + 3;      // [2] Q stage consumed by the MMA
+  uint64_t* s_full = bars + 5;       // [2] S = Q K^T complete
+  uint64_t* p_full = bars + 7;       // [2] P written by the 4 softmax warps
+  uint64_t* o_full = bars + 9;       // [2] O = P V complete
+  uint64_t* buf_free = bars + 11;    // [2] epilogue done with the TMEM buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5;
-  const int lane = tid & 31;
-  const int q0 = blockIdx.x * TQ;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int sample = blockIdx.z;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int my_tiles = (a.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
 
-  if (tid == 0) {
+  if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
-    mbar_init(qk_bar, 1);
-    mbar_init(v_bar, 1);
-    mbar_init(s_bar, 1);
-    mbar_init(o_bar, 1);
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 4);
+      mbar_init(&o_full[s], 1);
+      mbar_init(&buf_free[s], 4);
+    }
     fence_mbar_init();
   }
-  if (warp == 0) {
+  if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -87,118 +103,155 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (tid == 0) {
-    const int ctx_row = a.ctx_index[sample] * a.t_pad;
-    mbar_expect_tx(qk_bar, Cfg::NCHUNK * (Q_CHUNK_BYTES + KV_CHUNK_BYTES));
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      const int ctx_row = a.ctx_index[sample] * a.t_pad;
+      mbar_expect_tx(kv_full, 2 * Cfg::NCHUNK * KV_CHUNK_BYTES);
 #pragma unroll
-    for (int c = 0; c < Cfg::NCHUNK; ++c) {
-      tma_load_4d(sq + c * Q_CHUNK_BYTES, &tm_q, qk_bar, c * 64, head, q0, sample);
-      tma_load_3d(sk + c * KV_CHUNK_BYTES, &tm_k, qk_bar, c * 64, head, ctx_row);
-    }
-    mbar_expect_tx(v_bar, Cfg::NCHUNK * KV_CHUNK_BYTES);
+      for (int c = 0; c < Cfg::NCHUNK; ++c) {
+        tma_load_3d(sk + c * KV_CHUNK_BYTES, &tm_k, kv_full, c * 64, head, ctx_row);
+        tma_load_3d(sv + c * KV_CHUNK_BYTES, &tm_v, kv_full, c * 64, head, ctx_row);
+      }
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&q_empty[s], ph ^ 1);
+        mbar_expect_tx(&q_full[s], Cfg::Q_STAGE_BYTES);
+        const int q0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TQ;
 #pragma unroll
-    for (int c = 0; c < Cfg::NCHUNK; ++c)
-      tma_load_3d(sv + c * KV_CHUNK_BYTES, &tm_v, v_bar, c * 64, head, ctx_row);
-
-    // S = Q K^T
-    mbar_wait(qk_bar, 0);
-    tc_fence_after();
-    constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, TQ, TKV, 0, 0);
-#pragma unroll
-    for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
-      const int c = ks >> 2, kk = ks & 3;
-      const uint64_t qd = umma_desc_sw128(smem_u32(sq + c * Q_CHUNK_BYTES), 16, 1024) + 2 * kk;
-      const uint64_t kd = umma_desc_sw128(smem_u32(sk + c * KV_CHUNK_BYTES), 16, 1024) + 2 * kk;
-      mma_f16_ss(tmem_base, qd, kd, idesc_s, ks != 0);
-    }
-    tc_commit(s_bar);
-  }
-  __syncwarp();
-
-  // ---- softmax over the keys: one TMEM lane per thread
-  mbar_wait(s_bar, 0);
-  tc_fence_after();
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-  float p[TKV];
-#pragma unroll
-  for (int c = 0; c < TKV; c += 16) {
-    uint32_t v[16];
-    tmem_ld_x16(tmem_base + lane_addr + c, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 16; ++q) p[c + q] = __uint_as_float(v[q]);
-  }
-  float mx = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < TKV; ++j) {
-    p[j] = (j < a.t_valid) ? p[j] * a.scale_log2e : -INFINITY;
-    mx = fmaxf(mx, p[j]);
-  }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < TKV; ++j) {
-    p[j] = exp2f(p[j] - mx);  // masked keys: exp2(-inf) = 0
-    sum += p[j];
-  }
-#pragma unroll
-  for (int c = 0; c < TKV / 2; c += 8) {
-    uint32_t pk[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      __nv_bfloat162 b = __floats2bfloat162_rn(p[2 * (c + q)], p[2 * (c + q) + 1]);
-      pk[q] = *reinterpret_cast<uint32_t*>(&b);
-    }
-    tmem_st_x8(tmem_base + lane_addr + c, pk);
-  }
-  tmem_st_wait();
-  tc_fence_before();
-  __syncthreads();
-
-  // ---- O = P V
-  if (tid == 0) {
-    tc_fence_after();
-    mbar_wait(v_bar, 0);
-    tc_fence_after();
-    constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, TQ, Cfg::NPV, 0, 1);  // B (= V) is MN-major
-#pragma unroll
-    for (int j = 0; j < TKV / 16; ++j) {
-      // 16 keys = two 8-row groups (SBO = 1024 B); next 64-wide d chunk LBO = KV_CHUNK_BYTES away
-      const uint64_t vd = umma_desc_sw128(smem_u32(sv + j * 2048), KV_CHUNK_BYTES, 1024);
-      mma_f16_ts(tmem_base + O_COL, tmem_base + 8 * j, vd, idesc_o, j != 0);
-    }
-    tc_commit(o_bar);
-  }
-  __syncwarp();
-
-  mbar_wait(o_bar, 0);
-  tc_fence_after();
-  {
-    const int row = warp * 32 + lane;
-    const int q = q0 + row;
-    const float inv = 1.0f / sum;
-    __nv_bfloat16* dst =
-        a.out + (static_cast<size_t>(sample) * a.n_q + q) * (static_cast<size_t>(a.heads) * DH) + head * DH;
-#pragma unroll
-    for (int c = 0; c < Cfg::NPV; c += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + lane_addr + O_COL + c, v);
-      tmem_ld_wait();
-      if (q < a.n_q) {
-        uint32_t pk[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          __nv_bfloat162 b =
-              __floats2bfloat162_rn(__uint_as_float(v[2 * k]) * inv, __uint_as_float(v[2 * k + 1]) * inv);
-          pk[k] = *reinterpret_cast<uint32_t*>(&b);
-        }
-        if (c + 8 <= DH) *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (c + 16 <= DH) *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int c = 0; c < Cfg::NCHUNK; ++c)
+          tma_load_4d(sq + s * Cfg::Q_STAGE_BYTES + c * Q_CHUNK_BYTES, &tm_q, &q_full[s], c * 64, head, q0,
+                      sample);
       }
     }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = umma_idesc(UMMA_BF16, TQ, TKV, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, TQ, Cfg::NPV, 0, 1);  // B (= V) MN-major
+      auto issue_pv = [&](int j) {
+        const int b = j & 1;
+        mbar_wait(&p_full[b], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
+#pragma unroll
+        for (int k = 0; k < TKV / 16; ++k) {
+          // 16 keys = two 8-row groups (SBO = 1024 B); next 64-wide d chunk LBO = KV_CHUNK_BYTES away
+          const uint64_t vd = umma_desc_sw128(smem_u32(sv + k * 2048), KV_CHUNK_BYTES, 1024);
+          mma_f16_ts(buf + O_COL, buf + 8 * k, vd, idesc_o, k != 0);
+        }
+        tc_commit(&o_full[b]);
+      };
+      mbar_wait(kv_full, 0);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int b = i & 1;
+        const uint32_t ph = (i >> 1) & 1;
+        mbar_wait(&q_full[b], ph);
+        mbar_wait(&buf_free[b], ph ^ 1);
+        tc_fence_after();
+        const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
+        const uint8_t* qs = sq + b * Cfg::Q_STAGE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
+          const int c = ks >> 2, kk = ks & 3;
+          const uint64_t qd = umma_desc_sw128(smem_u32(qs + c * Q_CHUNK_BYTES), 16, 1024) + 2 * kk;
+          const uint64_t kd = umma_desc_sw128(smem_u32(sk + c * KV_CHUNK_BYTES), 16, 1024) + 2 * kk;
+          mma_f16_ss(buf, qd, kd, idesc_s, ks != 0);
+        }
+        tc_commit(&s_full[b]);
+        tc_commit(&q_empty[b]);
+        if (i >= 1) issue_pv(i - 1);
+      }
+      if (my_tiles >= 1) issue_pv(my_tiles - 1);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32)
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    float sum_prev = 1.f;
+
+    auto epilogue = [&](int j, float sum) {
+      const int b = j & 1;
+      mbar_wait(&o_full[b], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr + O_COL;
+      const int q = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * TQ + row;
+      const float inv = 1.0f / sum;
+      __nv_bfloat16* dst =
+          a.out + (static_cast<size_t>(sample) * a.n_q + q) * (static_cast<size_t>(a.heads) * DH) + head * DH;
+#pragma unroll
+      for (int c = 0; c < Cfg::NPV; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(buf + c, v);
+        tmem_ld_wait();
+        if (q < a.n_q) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            __nv_bfloat162 o =
+                __floats2bfloat162_rn(__uint_as_float(v[2 * k]) * inv, __uint_as_float(v[2 * k + 1]) * inv);
+            pk[k] = *reinterpret_cast<uint32_t*>(&o);
+          }
+          if (c + 8 <= DH) *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          if (c + 16 <= DH) *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&buf_free[b]);
+    };
+
+    for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&s_full[b], (i >> 1) & 1);
+      tc_fence_after();
+      const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr;
+      float p[TKV];
+#pragma unroll
+      for (int c = 0; c < TKV; c += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(buf + c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 16; ++q) p[c + q] = __uint_as_float(v[q]);
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < TKV; ++j) {
+        p[j] = (j < a.t_valid) ? p[j] * a.scale_log2e : -INFINITY;
+        mx = fmaxf(mx, p[j]);
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < TKV; ++j) {
+        p[j] = exp2f(p[j] - mx);  // masked keys: exp2(-inf) = 0
+        sum += p[j];
+      }
+#pragma unroll
+      for (int c = 0; c < TKV / 2; c += 8) {
+        uint32_t pk[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          __nv_bfloat162 o = __floats2bfloat162_rn(p[2 * (c + q)], p[2 * (c + q) + 1]);
+          pk[q] = *reinterpret_cast<uint32_t*>(&o);
+        }
+        tmem_st_x8(buf + c, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[b]);
+      // epilogue of the previous tile while this tile's P V runs
+      if (i >= 1) epilogue(i - 1, sum_prev);
+      sum_prev = sum;
+    }
+    if (my_tiles >= 1) epilogue(my_tiles - 1, sum_prev);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -259,6 +312,8 @@ extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, in
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_cross_attn: cannot query SM count");
   K3Args a;
   a.ctx_index = ctx_index_dev;
   a.out = static_cast<__nv_bfloat16*>(out_bf16_dev);
@@ -266,8 +321,14 @@ extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, in
   a.heads = heads;
   a.t_valid = t_valid;
   a.t_pad = t_pad;
+  a.n_tiles = (n_q + TQ - 1) / TQ;
   a.scale_log2e = scale * 1.4426950408889634f;
-  dim3 grid((n_q + TQ - 1) / TQ, heads, n_samples);
+  // CTAs per (sample, head): enough to cover ~2 CTAs per SM, each walking over >= 1 query tile
+  const int pairs = heads * n_samples;
+  int per_pair = (2 * sms + pairs - 1) / pairs;
+  if (per_pair > a.n_tiles) per_pair = a.n_tiles;
+  if (per_pair < 1) per_pair = 1;
+  dim3 grid(per_pair, heads, n_samples);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (d_head == 40) return launch_k3<40>(tq, tk, tv, a, grid, st);
   if (d_head == 80) return launch_k3<80>(tq, tk, tv, a, grid, st);
