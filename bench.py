@@ -281,6 +281,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-kernels', action='store_true', help='skip kernel microbenches')
+    ap.add_argument('--kernels-only', action='store_true',
+                    help='development aid: only the kernel roofline section')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -316,6 +318,9 @@ def main():
     peaks = _peaks()
 
     unet = factory.build_unet(dev, torch.bfloat16, seed=0)
+    if args.kernels_only:
+        print(json.dumps(kernel_rooflines(dev, unet, peaks)))
+        return
     vae = factory.build_vae(dev, torch.bfloat16, seed=1)
     B = 1
     g = torch.Generator().manual_seed(1234 + rank)

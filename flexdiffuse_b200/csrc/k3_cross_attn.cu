@@ -116,7 +116,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       for (int i = 0; i < my_tiles; ++i) {
         const int s = i & 1;
         const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&q_empty[s], ph ^ 1);
+        mbar_wait_backoff(&q_empty[s], ph ^ 1);
         mbar_expect_tx(&q_full[s], Cfg::Q_STAGE_BYTES);
         const int q0 = (static_cast<int>(blockIdx.x) + i * static_cast<int>(gridDim.x)) * TQ;
 #pragma unroll
@@ -132,7 +132,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       constexpr uint32_t idesc_o = umma_idesc(UMMA_BF16, TQ, Cfg::NPV, 0, 1);  // B (= V) MN-major
       auto issue_pv = [&](int j) {
         const int b = j & 1;
-        mbar_wait(&p_full[b], (j >> 1) & 1);
+        mbar_wait_backoff(&p_full[b], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
 #pragma unroll
@@ -143,12 +143,12 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         }
         tc_commit(&o_full[b]);
       };
-      mbar_wait(kv_full, 0);
+      mbar_wait_backoff(kv_full, 0);
       for (int i = 0; i < my_tiles; ++i) {
         const int b = i & 1;
         const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(&q_full[b], ph);
-        mbar_wait(&buf_free[b], ph ^ 1);
+        mbar_wait_backoff(&q_full[b], ph);
+        mbar_wait_backoff(&buf_free[b], ph ^ 1);
         tc_fence_after();
         const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
         const uint8_t* qs = sq + b * Cfg::Q_STAGE_BYTES;
@@ -217,18 +217,31 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 #pragma unroll
         for (int q = 0; q < 16; ++q) p[c + q] = __uint_as_float(v[q]);
       }
-      float mx = -INFINITY;
+      // keys >= t_valid only exist in the last 16 columns (t_valid > 64 is checked on the host)
 #pragma unroll
-      for (int j = 0; j < TKV; ++j) {
-        p[j] = (j < a.t_valid) ? p[j] * a.scale_log2e : -INFINITY;
-        mx = fmaxf(mx, p[j]);
-      }
-      float sum = 0.f;
+      for (int j = TKV - 16; j < TKV; ++j)
+        if (j >= a.t_valid) p[j] = -INFINITY;
+      float m0 = p[0], m1 = p[1];
 #pragma unroll
-      for (int j = 0; j < TKV; ++j) {
-        p[j] = exp2f(p[j] - mx);  // masked keys: exp2(-inf) = 0
-        sum += p[j];
+      for (int j = 2; j < TKV; j += 2) {
+        m0 = fmaxf(m0, p[j]);
+        m1 = fmaxf(m1, p[j + 1]);
       }
+      // exp2(s * scale*log2e - max * scale*log2e): one FFMA + one MUFU per key (scale > 0)
+      const float nmx = -fmaxf(m0, m1) * a.scale_log2e;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < TKV; j += 4) {
+        p[j] = ex2_approx(fmaf(p[j], a.scale_log2e, nmx));
+        p[j + 1] = ex2_approx(fmaf(p[j + 1], a.scale_log2e, nmx));
+        p[j + 2] = ex2_approx(fmaf(p[j + 2], a.scale_log2e, nmx));
+        p[j + 3] = ex2_approx(fmaf(p[j + 3], a.scale_log2e, nmx));
+        s0 += p[j];
+        s1 += p[j + 1];
+        s2 += p[j + 2];
+        s3 += p[j + 3];
+      }
+      const float sum = (s0 + s1) + (s2 + s3);
 #pragma unroll
       for (int c = 0; c < TKV / 2; c += 8) {
         uint32_t pk[8];
@@ -278,8 +291,9 @@ extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, in
   FD_REQUIRE(q_bf16_dev && kv_bf16_dev && ctx_index_dev && out_bf16_dev, "fd_cross_attn: NULL pointer");
   FD_REQUIRE(n_samples > 0 && n_q > 0 && heads > 0, "fd_cross_attn: non-positive shape");
   FD_REQUIRE(d_head == 40 || d_head == 80 || d_head == 160, "fd_cross_attn: d_head=%d not in {40, 80, 160}", d_head);
-  FD_REQUIRE(t_pad == TKV && t_valid >= 1 && t_valid <= t_pad, "fd_cross_attn: need t_pad == %d and 1 <= t_valid <= t_pad",
-             TKV);
+  FD_REQUIRE(t_pad == TKV && t_valid > TKV - 16 && t_valid <= t_pad,
+             "fd_cross_attn: need t_pad == %d and %d < t_valid <= t_pad", TKV, TKV - 16);
+  FD_REQUIRE(scale > 0.f, "fd_cross_attn: scale must be positive");
   FD_REQUIRE(k_col_off % 8 == 0 && v_col_off % 8 == 0 && kv_row_stride % 8 == 0,
              "fd_cross_attn: column offsets / row stride must be multiples of 8 elements");
   FD_REQUIRE(k_col_off + heads * d_head <= kv_row_stride && v_col_off + heads * d_head <= kv_row_stride,
