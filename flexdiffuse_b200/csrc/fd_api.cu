@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "fd_common.cuh"
 
@@ -19,26 +20,88 @@ int set_error(int code, const char* fmt, ...) {
 }
 
 int check_device() {
+  static thread_local int ok_device = -1;  // last device that passed the gate on this thread
   int dev = -1;
   cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess && dev == ok_device) return FD_OK;
   if (e != cudaSuccess) {
     cudaGetLastError();
     return set_error(FD_ERR_ARCH, "no CUDA device: %s (flexdiffuse_b200 has no CPU fallback)",
                      cudaGetErrorString(e));
   }
-  return fd_arch_check(dev);
+  const int rc = fd_arch_check(dev);
+  if (rc == FD_OK) ok_device = dev;
+  return rc;
 }
 
 int sm_count() {
+  static thread_local int cached_dev = -1, cached_n = 0;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (dev == cached_dev) return cached_n;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+  cached_dev = dev;
+  cached_n = n;
   return n;
 }
+
+namespace {
+// Encoding a tensor map costs a few microseconds of host time; the same (pointer, shape) pairs
+// recur every denoising step (the caching allocator hands back the same blocks), so keep a small
+// thread-local direct-mapped cache.  A tensor map only describes addresses and strides, so a
+// stale entry for a re-used pointer with identical geometry is still correct.
+struct TmapKey {
+  const void* base;
+  uint64_t dims[5], strides[4];
+  uint32_t box[5], rank, dtype, swizzle;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapEntry {
+  bool valid = false;
+  TmapKey key;
+  CUtensorMap map;
+};
+constexpr int TMAP_CACHE = 256;
+thread_local TmapEntry g_tmap_cache[TMAP_CACHE];
+}  // namespace
+
+static int encode_tmap_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
+                                const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                CUtensorMapSwizzle swizzle);
 
 int encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
                 const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
                 CUtensorMapSwizzle swizzle) {
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  key.dtype = static_cast<uint32_t>(dtype);
+  key.swizzle = static_cast<uint32_t>(swizzle);
+  uint64_t h = reinterpret_cast<uint64_t>(base) * 0x9E3779B97F4A7C15ull;
+  for (uint32_t i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i + 1 < rank) key.strides[i] = strides_bytes[i];
+    h = (h ^ (dims[i] * 31 + box[i])) * 0x9E3779B97F4A7C15ull;
+  }
+  TmapEntry& e = g_tmap_cache[(h >> 40) % TMAP_CACHE];
+  if (e.valid && e.key == key) {
+    *map = e.map;
+    return FD_OK;
+  }
+  int rc = encode_tmap_uncached(map, dtype, rank, base, dims, strides_bytes, box, swizzle);
+  if (rc == FD_OK) {
+    e.valid = true;
+    e.key = key;
+    e.map = *map;
+  }
+  return rc;
+}
+
+static int encode_tmap_uncached(CUtensorMap* map, CUtensorMapDataType dtype, uint32_t rank, const void* base,
+                                const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                                CUtensorMapSwizzle swizzle) {
   static thread_local PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   if (!encode) {
     void* fn = nullptr;

@@ -43,7 +43,23 @@ struct K3Cfg {
   static constexpr int SMEM = 1024 + QSTAGES * Q_STAGE_BYTES + 2 * NCHUNK * KV_CHUNK_BYTES + 256;
 };
 
+// development aid: when set (fd_debug_set_k3_timing), CTA (0,0,0) records %globaltimer (ns) at its
+// phase boundaries: [0] start, [1] setup done, [2] K/V+Q0 landed, [3] S0 ready, [4] P0 written,
+// [5] O0 ready, [6] epilogue 0 done, [7] kernel end
+static long long* g_k3_timing = nullptr;
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define K3_STAMP(slot)                                                                  \
+  do {                                                                                  \
+    if (a.timing && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) a.timing[slot] = gtime(); \
+  } while (0)
+
 struct K3Args {
+  long long* timing;
   const int32_t* ctx_index;
   __nv_bfloat16* out;
   int n_q, heads, t_valid, t_pad, n_tiles;
@@ -75,6 +91,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int head = blockIdx.y;
   const int sample = blockIdx.z;
+  if (threadIdx.x == 0) K3_STAMP(0);
   // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int my_tiles = (a.n_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
@@ -102,6 +119,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) K3_STAMP(1);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -148,6 +166,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const int b = i & 1;
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait_backoff(&q_full[b], ph);
+        if (i == 0) K3_STAMP(2);
         mbar_wait_backoff(&buf_free[b], ph ^ 1);
         tc_fence_after();
         const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
@@ -176,46 +195,59 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       const int b = j & 1;
       mbar_wait(&o_full[b], (j >> 1) & 1);
       tc_fence_after();
+      if (j == 0 && threadIdx.x == 64) K3_STAMP(5);
       const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr + O_COL;
       const int q = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * TQ + row;
       const float inv = 1.0f / sum;
       __nv_bfloat16* dst =
           a.out + (static_cast<size_t>(sample) * a.n_q + q) * (static_cast<size_t>(a.heads) * DH) + head * DH;
+      constexpr int GROUP = 3;  // 16-column loads in flight per wait (48 registers)
 #pragma unroll
-      for (int c = 0; c < Cfg::NPV; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(buf + c, v);
+      for (int c0 = 0; c0 < Cfg::NPV; c0 += 16 * GROUP) {
+        uint32_t v[GROUP][16];
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g)
+          if (c0 + 16 * g < Cfg::NPV) tmem_ld_x16(buf + c0 + 16 * g, v[g]);
         tmem_ld_wait();
-        if (q < a.n_q) {
-          uint32_t pk[8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            __nv_bfloat162 o =
-                __floats2bfloat162_rn(__uint_as_float(v[2 * k]) * inv, __uint_as_float(v[2 * k + 1]) * inv);
-            pk[k] = *reinterpret_cast<uint32_t*>(&o);
+        for (int g = 0; g < GROUP; ++g) {
+          const int c = c0 + 16 * g;
+          if (c < Cfg::NPV && q < a.n_q) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              __nv_bfloat162 o = __floats2bfloat162_rn(__uint_as_float(v[g][2 * k]) * inv,
+                                                       __uint_as_float(v[g][2 * k + 1]) * inv);
+              pk[k] = *reinterpret_cast<uint32_t*>(&o);
+            }
+            if (c + 8 <= DH) *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (c + 16 <= DH) *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
           }
-          if (c + 8 <= DH) *reinterpret_cast<uint4*>(dst + c) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          if (c + 16 <= DH) *reinterpret_cast<uint4*>(dst + c + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&buf_free[b]);
+      if (j == 0 && threadIdx.x == 64) K3_STAMP(6);
     };
 
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
+      if (i == 0 && threadIdx.x == 64) K3_STAMP(3);
       const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr;
       float p[TKV];
+      {
+        // all five 16-column loads in flight, one wait
+        uint32_t v[TKV / 16][16];
 #pragma unroll
-      for (int c = 0; c < TKV; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(buf + c, v);
+        for (int c = 0; c < TKV / 16; ++c) tmem_ld_x16(buf + 16 * c, v[c]);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) p[c + q] = __uint_as_float(v[q]);
+        for (int c = 0; c < TKV / 16; ++c)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) p[16 * c + q] = __uint_as_float(v[c][q]);
       }
       // keys >= t_valid only exist in the last 16 columns (t_valid > 64 is checked on the host)
 #pragma unroll
@@ -256,6 +288,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[b]);
+      if (i == 0 && threadIdx.x == 64) K3_STAMP(4);
       // epilogue of the previous tile while this tile's P V runs
       if (i >= 1) epilogue(i - 1, sum_prev);
       sum_prev = sum;
@@ -268,13 +301,20 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (threadIdx.x == 0) K3_STAMP(7);
 }
 
 template <int DH>
 int launch_k3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const K3Args& a, dim3 grid,
               cudaStream_t st) {
   using Cfg = K3Cfg<DH>;
-  FD_CUDA_OK(cudaFuncSetAttribute(k3_cross_attn_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  static thread_local int attr_device = -1;  // the attribute is per device; set it once per thread/device
+  int dev = 0;
+  FD_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_device != dev) {
+    FD_CUDA_OK(cudaFuncSetAttribute(k3_cross_attn_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_device = dev;
+  }
   k3_cross_attn_kernel<DH><<<grid, K3_THREADS, Cfg::SMEM, st>>>(tq, tk, tv, a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
@@ -282,6 +322,9 @@ int launch_k3(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
 
 }  // namespace
 }  // namespace fd
+
+// development aid (not part of the product ABI): device buffer of >= 8 int64 for phase timestamps
+extern "C" void fd_debug_set_k3_timing(void* buf_dev) { fd::g_k3_timing = static_cast<long long*>(buf_dev); }
 
 extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, int64_t kv_rows, int64_t kv_row_stride,
                              int k_col_off, int v_col_off, const int32_t* ctx_index_dev, int n_samples, int n_q,
@@ -329,6 +372,7 @@ extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, in
   const int sms = sm_count();
   if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_cross_attn: cannot query SM count");
   K3Args a;
+  a.timing = g_k3_timing;
   a.ctx_index = ctx_index_dev;
   a.out = static_cast<__nv_bfloat16*>(out_bf16_dev);
   a.n_q = n_q;
