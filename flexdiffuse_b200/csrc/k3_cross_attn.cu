@@ -17,8 +17,10 @@
 //                   so the P V latency is hidden.
 //   S = Q K^T : M=128, N=80, K=d (k-steps of 16)   both operands K-major SWIZZLE_128B in smem
 //   O = P V   : M=128, N=d (rounded to 16), K=80   A = P from TMEM, B = V MN-major in smem
-// TMEM: two buffers; in each  S [0,80) fp32,  P [0,40) bf16x2 aliasing S,  O [40, 40+N)
-// (S is dead once P is written).  HBM-bound by design (AI = 77 FLOP/B).
+// TMEM: S0 [0,80) and S1 [80,160) fp32 (P = bf16x2 in the first 40 columns of its S buffer),
+// one O accumulator [160, 160+N).  S is double-buffered so S_{i+1} is computed under the softmax
+// of tile i; O needs only one buffer because the epilogue of tile i runs before P V of tile i+1
+// is issued.  HBM-bound by design (AI = 77 FLOP/B).
 #include "fd_common.cuh"
 
 namespace fd {
@@ -29,7 +31,6 @@ constexpr int TKV = 80;     // keys padded 77 -> 80
 constexpr int K3_THREADS = 192;
 constexpr int Q_CHUNK_BYTES = TQ * 128;
 constexpr int KV_CHUNK_BYTES = TKV * 128;
-constexpr int O_COL = 40;
 constexpr int QSTAGES = 2;
 
 template <int DH>
@@ -37,8 +38,11 @@ struct K3Cfg {
   static constexpr int NCHUNK = (DH + 63) / 64;        // 64-element d chunks (128 B swizzle rows)
   static constexpr int KSTEPS = (DH + 15) / 16;        // UMMA k-steps for Q K^T
   static constexpr int NPV = ((DH + 15) / 16) * 16;    // UMMA N for P V
-  static constexpr int BUF_COLS = O_COL + NPV;         // TMEM columns per accumulator buffer
-  static constexpr int TMEM_COLS = 2 * BUF_COLS <= 256 ? 256 : 512;
+  static constexpr int SMEM_EST = 1024 + 2 * ((DH + 63) / 64) * (TQ * 128) + 2 * ((DH + 63) / 64) * (TKV * 128) + 256;
+  static constexpr int S_COLS = TKV;                   // one S / P buffer
+  static constexpr int O_BASE = 2 * S_COLS;            // O accumulator after the two S buffers
+  static constexpr int TMEM_COLS = O_BASE + NPV <= 256 ? 256 : 512;
+  static constexpr int CTAS_PER_SM = (O_BASE + NPV <= 256 && SMEM_EST <= 110 * 1024) ? 2 : 1;
   static constexpr int Q_STAGE_BYTES = NCHUNK * Q_CHUNK_BYTES;
   static constexpr int SMEM = 1024 + QSTAGES * Q_STAGE_BYTES + 2 * NCHUNK * KV_CHUNK_BYTES + 256;
 };
@@ -83,9 +87,9 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   uint64_t* q_empty = bars + 3;      // [2] Q stage consumed by the MMA
   uint64_t* s_full = bars + 5;       // [2] S = Q K^T complete
   uint64_t* p_full = bars + 7;       // [2] P written by the 4 softmax warps
-  uint64_t* o_full = bars + 9;       // [2] O = P V complete
-  uint64_t* buf_free = bars + 11;    // [2] epilogue done with the TMEM buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* o_full = bars + 9;       // O = P V complete
+  uint64_t* o_free = bars + 10;      // epilogue has drained O
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -106,9 +110,9 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 4);
-      mbar_init(&o_full[s], 1);
-      mbar_init(&buf_free[s], 4);
     }
+    mbar_init(o_full, 1);
+    mbar_init(o_free, 4);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -151,15 +155,16 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       auto issue_pv = [&](int j) {
         const int b = j & 1;
         mbar_wait_backoff(&p_full[b], (j >> 1) & 1);
+        if (j >= 1) mbar_wait_backoff(o_free, (j - 1) & 1);  // epilogue of tile j-1 drained O
         tc_fence_after();
-        const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
+        const uint32_t pbuf = tmem_base + b * Cfg::S_COLS;
 #pragma unroll
         for (int k = 0; k < TKV / 16; ++k) {
           // 16 keys = two 8-row groups (SBO = 1024 B); next 64-wide d chunk LBO = KV_CHUNK_BYTES away
           const uint64_t vd = umma_desc_sw128(smem_u32(sv + k * 2048), KV_CHUNK_BYTES, 1024);
-          mma_f16_ts(buf + O_COL, buf + 8 * k, vd, idesc_o, k != 0);
+          mma_f16_ts(tmem_base + Cfg::O_BASE, pbuf + 8 * k, vd, idesc_o, k != 0);
         }
-        tc_commit(&o_full[b]);
+        tc_commit(o_full);
       };
       mbar_wait_backoff(kv_full, 0);
       for (int i = 0; i < my_tiles; ++i) {
@@ -167,9 +172,10 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         const uint32_t ph = (i >> 1) & 1;
         mbar_wait_backoff(&q_full[b], ph);
         if (i == 0) K3_STAMP(2);
-        mbar_wait_backoff(&buf_free[b], ph ^ 1);
+        // S buffer b was last read by P V of tile i-2, issued earlier by this thread: the tensor
+        // pipe executes in issue order, so no extra wait is needed before overwriting it
         tc_fence_after();
-        const uint32_t buf = tmem_base + b * Cfg::BUF_COLS;
+        const uint32_t buf = tmem_base + b * Cfg::S_COLS;
         const uint8_t* qs = sq + b * Cfg::Q_STAGE_BYTES;
 #pragma unroll
         for (int ks = 0; ks < Cfg::KSTEPS; ++ks) {
@@ -192,11 +198,10 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     float sum_prev = 1.f;
 
     auto epilogue = [&](int j, float sum) {
-      const int b = j & 1;
-      mbar_wait(&o_full[b], (j >> 1) & 1);
+      mbar_wait(o_full, j & 1);
       tc_fence_after();
       if (j == 0 && threadIdx.x == 64) K3_STAMP(5);
-      const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr + O_COL;
+      const uint32_t buf = tmem_base + lane_addr + Cfg::O_BASE;
       const int q = (static_cast<int>(blockIdx.x) + j * static_cast<int>(gridDim.x)) * TQ + row;
       const float inv = 1.0f / sum;
       __nv_bfloat16* dst =
@@ -227,7 +232,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&buf_free[b]);
+      if (lane == 0) mbar_arrive(o_free);
       if (j == 0 && threadIdx.x == 64) K3_STAMP(6);
     };
 
@@ -236,7 +241,7 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       mbar_wait(&s_full[b], (i >> 1) & 1);
       tc_fence_after();
       if (i == 0 && threadIdx.x == 64) K3_STAMP(3);
-      const uint32_t buf = tmem_base + b * Cfg::BUF_COLS + lane_addr;
+      const uint32_t buf = tmem_base + b * Cfg::S_COLS + lane_addr;
       float p[TKV];
       {
         // all five 16-column loads in flight, one wait
@@ -381,9 +386,11 @@ extern "C" int fd_cross_attn(const void* q_bf16_dev, const void* kv_bf16_dev, in
   a.t_pad = t_pad;
   a.n_tiles = (n_q + TQ - 1) / TQ;
   a.scale_log2e = scale * 1.4426950408889634f;
-  // CTAs per (sample, head): enough to cover ~2 CTAs per SM, each walking over >= 1 query tile
+  // CTAs per (sample, head): fill the resident capacity once (no second wave), each CTA walking
+  // over >= 1 query tile
   const int pairs = heads * n_samples;
-  int per_pair = (2 * sms + pairs - 1) / pairs;
+  const int per_sm = d_head == 160 ? K3Cfg<160>::CTAS_PER_SM : (d_head == 80 ? K3Cfg<80>::CTAS_PER_SM : K3Cfg<40>::CTAS_PER_SM);
+  int per_pair = (per_sm * sms) / pairs;
   if (per_pair > a.n_tiles) per_pair = a.n_tiles;
   if (per_pair < 1) per_pair = 1;
   dim3 grid(per_pair, heads, n_samples);
