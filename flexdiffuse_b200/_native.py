@@ -26,7 +26,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
                'fd_kv_project', 'fd_cross_attn',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
-               'fd_add_bias_residual', 'fd_geglu')
+               'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu')
 
 
 class NativeError(RuntimeError):
@@ -99,9 +99,12 @@ def lib() -> C.CDLL:
     l.fd_add_bias_residual.restype = C.c_int
     l.fd_groupnorm_act.argtypes = [
         vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
-        C.c_int, vp
+        C.c_int, C.c_int64, vp
     ]
     l.fd_groupnorm_act.restype = C.c_int
+    l.fd_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int,
+                                   C.c_float, vp]
+    l.fd_add_layernorm.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
     l.fd_geglu.restype = C.c_int
     if l.fd_version() != FD_ABI_VERSION:
@@ -303,10 +306,13 @@ def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
     N, Cc, H, W = x.shape
+    bias_stride = 0
     if bias is not None:
-        _need(bias, 'bias', torch.bfloat16)
-        if tuple(bias.shape) != (N, Cc):
-            raise NativeError(f'bias must be [{N},{Cc}]')
+        if (not bias.is_cuda or bias.dtype != torch.bfloat16
+                or tuple(bias.shape) != (N, Cc) or bias.stride(1) != 1):
+            raise NativeError(f'bias must be CUDA bfloat16 [{N},{Cc}] with unit '
+                              'column stride')
+        bias_stride = bias.stride(0) if N > 1 else Cc
     y = torch.empty_like(x)  # preserves channels_last
     nbytes = lib().fd_groupnorm_act_workspace_bytes(N, H * W, Cc, groups)
     ws = _gn_workspaces.get(x.device)
@@ -314,13 +320,13 @@ def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
         # one grow-only scratch per device; launches on a stream are ordered, so reuse is safe
         if ws is not None:
             _gn_retired.append(ws)  # a captured CUDA graph may still point at it
-        ws = torch.empty(max(2 * nbytes, 1 << 24), dtype=torch.uint8, device=x.device)
+        ws = torch.zeros(max(2 * nbytes, 1 << 24), dtype=torch.uint8, device=x.device)
         _gn_workspaces[x.device] = ws
     rc = lib().fd_groupnorm_act(ptr(x), ptr(bias), ptr(gamma), ptr(beta), ptr(ws),
                                 ptr(y), N, H * W, Cc, groups, float(eps),
-                                int(silu), stream_ptr(x.device))
+                                int(silu), bias_stride, stream_ptr(x.device))
     check(rc, 'fd_groupnorm_act')
-    count_launch(3)
+    count_launch(2)
     return y
 
 
@@ -353,3 +359,23 @@ def add_bias_residual(x: torch.Tensor, h: torch.Tensor,
     check(rc, 'fd_add_bias_residual')
     count_launch()
     return y
+
+
+def add_layernorm(x: torch.Tensor, y: Optional[torch.Tensor], gamma: torch.Tensor,
+                  beta: torch.Tensor, eps: float):
+    '''fd_add_layernorm.  Returns (x + y, LayerNorm(x + y)); with y None: (x, LayerNorm(x)).'''
+    _need(x, 'x', torch.bfloat16)
+    Cc = x.shape[-1]
+    norm = torch.empty_like(x)
+    total = None
+    if y is not None:
+        _need(y, 'y', torch.bfloat16)
+        if y.shape != x.shape:
+            raise NativeError('x / y shape mismatch')
+        total = torch.empty_like(x)
+    rc = lib().fd_add_layernorm(ptr(x), ptr(y), ptr(gamma), ptr(beta), ptr(total),
+                                ptr(norm), x.numel() // Cc, Cc, float(eps),
+                                stream_ptr(x.device))
+    check(rc, 'fd_add_layernorm')
+    count_launch()
+    return (total if y is not None else x), norm

@@ -9,8 +9,8 @@
 //   K5  y = act( GroupNorm( x + bias[n,c] ) * gamma[c] + beta[c] )        NHWC bf16 in / out
 //       diffusers ResnetBlock2D: norm1 -> SiLU, (+ time_emb_proj) -> norm2 -> SiLU;
 //       SpatialTransformer.norm, conv_norm_out.  Two launches: per-slab partial (sum, sumsq) per
-//       channel pair, a tiny per-group finalise, then normalise + affine + SiLU: three launches, no
-//       atomics, fixed summation order (bit-reproducible).
+//       channel pair (the last CTA of a sample reduces them to mean / rstd), then normalise + affine +
+//       SiLU: two launches, fixed summation order (bit-reproducible).
 //   K7  y = x + h + bias[c]: the resnet residual add with conv2's bias folded in (cuDNN would
 //       otherwise add every convolution bias with a separate broadcast kernel).
 //   K6  out[m, f] = in[m, f] * gelu(in[m, F + f])                          diffusers GEGLU
@@ -23,18 +23,21 @@ namespace {
 
 constexpr int GN_THREADS = 256;   // 8 warps: warp w takes rows w, w+8, ... of the slab
 constexpr int GN_WARPS = GN_THREADS / 32;
-constexpr int GN_ROWS = 32;        // rows (pixels) per CTA
+constexpr int GN_ROWS = 32;        // rows (pixels) per CTA in the apply phase
+constexpr int GN_STAT_ROWS = 128;  // rows per CTA in the statistics phase
 constexpr int GN_MAX_GROUPS = 32;
 
 struct GnArgs {
   const __nv_bfloat16* x;      // [N, HW, C] (channels_last view of [N, C, H, W])
-  const __nv_bfloat16* bias;   // [N, C] or nullptr
+  const __nv_bfloat16* bias;   // [N, C] (row stride bias_stride elements) or nullptr
+  int64_t bias_stride;
   const __nv_bfloat16* gamma;  // [C]
   const __nv_bfloat16* beta;   // [C]
   float2* partial;             // [N, slabs, C/2]  per channel-pair (sum, sumsq) of one slab
   float2* stats;               // [N, G]           (mean, rstd)
+  int* counter;                // [N] ticket counters (zero between launches)
   __nv_bfloat16* y;            // [N, HW, C]
-  int HW, C, G, slabs;
+  int HW, C, G, slabs, stat_slabs;
   float eps;
   int act_silu;
 };
@@ -43,34 +46,40 @@ __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
 }
 
-// phase 1.  grid (C/64, slabs, N): one CTA = 32 channel pairs x 32 rows; a warp reads 128
-// contiguous bytes per row, 4 rows in flight per thread.  Fixed reduction order (no atomics).
+// phase 1 + 2.  grid (C/64, stat_slabs, N): one CTA = 32 channel pairs x 128 rows; a warp reads 128
+// contiguous bytes per row, 8 rows in flight per thread.  The LAST CTA of a sample to finish
+// (ticket counter, self-resetting) reduces that sample's partials to (mean, rstd) per group, so
+// no separate finalise launch is needed.  Every reduction has a fixed order: bit-reproducible.
 __global__ void __launch_bounds__(GN_THREADS) k5_gn_stats_kernel(const GnArgs a) {
   __shared__ float2 red[GN_WARPS][32];
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int pairs = a.C >> 1;
   const int p = blockIdx.x * 32 + lane;
   const int slab = blockIdx.y, n = blockIdx.z;
-  const int r0 = slab * GN_ROWS;
+  const int r0 = slab * GN_STAT_ROWS;
   const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + static_cast<size_t>(n) * a.HW * pairs + p;
   float2 b = make_float2(0.f, 0.f);
-  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias)[static_cast<size_t>(n) * pairs + p]);
-  uint32_t v[GN_ROWS / GN_WARPS];
-#pragma unroll
-  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
-    const int r = r0 + warp + i * GN_WARPS;
-    v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
-  }
+  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[p]);
   float s = 0.f, q = 0.f;
 #pragma unroll
-  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
-    const int r = r0 + warp + i * GN_WARPS;
-    if (r < a.HW) {
-      float2 f = bf2_to_f2(v[i]);
-      f.x += b.x;
-      f.y += b.y;
-      s += f.x + f.y;
-      q += f.x * f.x + f.y * f.y;
+  for (int half = 0; half < 2; ++half) {
+    uint32_t v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + warp + (half * 8 + i) * GN_WARPS;
+      v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = r0 + warp + (half * 8 + i) * GN_WARPS;
+      if (r < a.HW) {
+        float2 f = bf2_to_f2(v[i]);
+        f.x += b.x;
+        f.y += b.y;
+        s += f.x + f.y;
+        q += f.x * f.x + f.y * f.y;
+      }
     }
   }
   red[warp][lane] = make_float2(s, q);
@@ -82,38 +91,41 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_stats_kernel(const GnArgs a)
       t.x += red[w][lane].x;
       t.y += red[w][lane].y;
     }
-    a.partial[(static_cast<size_t>(n) * a.slabs + slab) * pairs + p] = t;
+    a.partial[(static_cast<size_t>(n) * a.stat_slabs + slab) * pairs + p] = t;
   }
-}
-
-// phase 2.  grid (G, N): reduce the partials of one group to (mean, rstd), fixed order.
-__global__ void __launch_bounds__(256) k5_gn_finalize_kernel(const GnArgs a) {
-  __shared__ float2 red[256];
-  const int g = blockIdx.x, n = blockIdx.y;
-  const int pairs = a.C >> 1, cg2 = (a.C / a.G) >> 1;
-  const int total = a.slabs * cg2;
-  float s = 0.f, q = 0.f;
-  for (int i = threadIdx.x; i < total; i += 256) {
-    const int slab = i / cg2, k = i - slab * cg2;
-    const float2 t = a.partial[(static_cast<size_t>(n) * a.slabs + slab) * pairs + g * cg2 + k];
-    s += t.x;
-    q += t.y;
-  }
-  red[threadIdx.x] = make_float2(s, q);
+  // ---- last CTA of this sample finalises
+  __threadfence();
   __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      red[threadIdx.x].x += red[threadIdx.x + o].x;
-      red[threadIdx.x].y += red[threadIdx.x + o].y;
-    }
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
-    const float mean = red[0].x / cnt;
-    const float var = fmaxf(red[0].y / cnt - mean * mean, 0.f);
-    a.stats[static_cast<size_t>(n) * a.G + g] = make_float2(mean, rsqrtf(var + a.eps));
+    const int ticket = atomicAdd(&a.counter[n], 1);
+    s_last = ticket == static_cast<int>(gridDim.x * gridDim.y) - 1;
   }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int cg2 = (a.C / a.G) >> 1;
+  const int total = a.stat_slabs * cg2;
+  const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
+  for (int g = warp; g < a.G; g += GN_WARPS) {
+    float ss = 0.f, qq = 0.f;
+    for (int i = lane; i < total; i += 32) {
+      const int sl = i / cg2, k = i - sl * cg2;
+      const float2 t = __ldcg(&a.partial[(static_cast<size_t>(n) * a.stat_slabs + sl) * pairs + g * cg2 + k]);
+      ss += t.x;
+      qq += t.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    }
+    if (lane == 0) {
+      const float mean = ss / cnt;
+      const float var = fmaxf(qq / cnt - mean * mean, 0.f);
+      a.stats[static_cast<size_t>(n) * a.G + g] = make_float2(mean, rsqrtf(var + a.eps));
+    }
+  }
+  if (threadIdx.x == 0) a.counter[n] = 0;  // ready for the next launch
 }
 
 // phase 3: normalise + affine + optional SiLU, same tiling as phase 1.
@@ -136,7 +148,7 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_apply_kernel(const GnArgs a)
   const float2 gam = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.gamma)[p]);
   const float2 bet = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.beta)[p]);
   float2 b = make_float2(0.f, 0.f);
-  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias)[static_cast<size_t>(n) * pairs + p]);
+  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[p]);
   // y = (x + b - mean) * rstd * gamma + beta  =  x * sc + sh
   const float scx = st.y * gam.x, scy = st.y * gam.y;
   const float shx = (b.x - st.x) * scx + bet.x, shy = (b.y - st.x) * scy + bet.y;
@@ -177,6 +189,65 @@ __global__ void __launch_bounds__(256) k7_add_bias_residual_kernel(const uint4* 
   }
 }
 
+// K8: s = x + y (optional), n = LayerNorm(s) * gamma + beta.  One warp per row of C channels
+// (C/64 bf16 pairs per lane, kept in registers: exact two-pass mean / variance).  Writes the
+// residual sum and the normalised row in the same pass (BasicTransformerBlock's
+// `x = attn(norm(x)) + x` followed by the next `norm(x)`).
+template <int PAIRS_PER_LANE>
+__global__ void __launch_bounds__(256) k8_add_layernorm_kernel(const uint32_t* __restrict__ x,
+                                                               const uint32_t* __restrict__ y,
+                                                               const uint32_t* __restrict__ gamma,
+                                                               const uint32_t* __restrict__ beta,
+                                                               uint32_t* __restrict__ sum_out,
+                                                               uint32_t* __restrict__ norm_out, int64_t M, float eps) {
+  constexpr int PAIRS = PAIRS_PER_LANE * 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const uint32_t* xr = x + row * PAIRS;
+  uint32_t xv[PAIRS_PER_LANE], yv[PAIRS_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < PAIRS_PER_LANE; ++i) xv[i] = xr[lane + 32 * i];
+  if (y) {
+    const uint32_t* yr = y + row * PAIRS;
+#pragma unroll
+    for (int i = 0; i < PAIRS_PER_LANE; ++i) yv[i] = yr[lane + 32 * i];
+  }
+  float2 v[PAIRS_PER_LANE];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+    v[i] = bf2_to_f2(xv[i]);
+    if (y) {
+      const float2 t = bf2_to_f2(yv[i]);
+      // the residual stream is bf16: normalise exactly what is stored
+      __nv_bfloat162 r = __floats2bfloat162_rn(v[i].x + t.x, v[i].y + t.y);
+      const uint32_t rb = *reinterpret_cast<uint32_t*>(&r);
+      if (sum_out) sum_out[row * PAIRS + lane + 32 * i] = rb;
+      v[i] = bf2_to_f2(rb);
+    }
+    s += v[i].x + v[i].y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (2.0f * PAIRS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+    const float dx = v[i].x - mean, dy = v[i].y - mean;
+    q += dx * dx + dy * dy;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (2.0f * PAIRS) + eps);
+#pragma unroll
+  for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+    const float2 g = bf2_to_f2(gamma[lane + 32 * i]), b = bf2_to_f2(beta[lane + 32 * i]);
+    __nv_bfloat162 o = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    norm_out[row * PAIRS + lane + 32 * i] = *reinterpret_cast<uint32_t*>(&o);
+  }
+}
+
 // K6: GEGLU.  in [M, 2F] bf16 -> out [M, F] bf16; 8 elements (16 B) per thread.
 __global__ void __launch_bounds__(256) k6_geglu_kernel(const __nv_bfloat16* __restrict__ in,
                                                        __nv_bfloat16* __restrict__ out, int64_t M, int F) {
@@ -205,16 +276,19 @@ __global__ void __launch_bounds__(256) k6_geglu_kernel(const __nv_bfloat16* __re
 }
 
 }  // namespace
+
+static inline int64_t gn_counter_bytes(int N) { return ((static_cast<int64_t>(N) * 4 + 255) / 256) * 256; }
 }  // namespace fd
 
 extern "C" int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G) {
-  const int64_t slabs = (HW + fd::GN_ROWS - 1) / fd::GN_ROWS;
-  return (static_cast<int64_t>(N) * slabs * (C / 2) + static_cast<int64_t>(N) * G) * 8;
+  // [N ticket counters (must be zero-initialised once)] [partials] [stats]
+  const int64_t slabs = (HW + fd::GN_STAT_ROWS - 1) / fd::GN_STAT_ROWS;
+  return fd::gn_counter_bytes(N) + (static_cast<int64_t>(N) * slabs * (C / 2) + static_cast<int64_t>(N) * G) * 8;
 }
 
 extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
                                 const void* beta_bf16_dev, void* workspace_dev, void* y_bf16_dev, int N, int HW,
-                                int C, int G, float eps, int act_silu, void* stream) {
+                                int C, int G, float eps, int act_silu, int64_t bias_row_stride, void* stream) {
   using namespace fd;
   FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && workspace_dev && y_bf16_dev,
              "fd_groupnorm_act: NULL pointer");
@@ -225,15 +299,22 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   const int slabs = (HW + GN_ROWS - 1) / GN_ROWS;
   FD_REQUIRE(N <= 65535 && slabs <= 65535, "fd_groupnorm_act: shape exceeds grid limits");
   FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 8 == 0, "fd_groupnorm_act: workspace must be 8-byte aligned");
+  FD_REQUIRE(!bias_bf16_dev || (bias_row_stride >= C && bias_row_stride % 2 == 0 &&
+                                reinterpret_cast<uintptr_t>(bias_bf16_dev) % 4 == 0),
+             "fd_groupnorm_act: bias row stride must be even and >= C, pointer 4-byte aligned");
   int rc = check_device();
   if (rc != FD_OK) return rc;
   GnArgs a;
   a.x = static_cast<const __nv_bfloat16*>(x_bf16_dev);
   a.bias = static_cast<const __nv_bfloat16*>(bias_bf16_dev);
+  a.bias_stride = bias_row_stride;
   a.gamma = static_cast<const __nv_bfloat16*>(gamma_bf16_dev);
   a.beta = static_cast<const __nv_bfloat16*>(beta_bf16_dev);
-  a.partial = static_cast<float2*>(workspace_dev);
-  a.stats = a.partial + static_cast<size_t>(N) * slabs * (C / 2);
+  const int stat_slabs = (HW + GN_STAT_ROWS - 1) / GN_STAT_ROWS;
+  a.counter = static_cast<int*>(workspace_dev);
+  a.partial = reinterpret_cast<float2*>(static_cast<char*>(workspace_dev) + gn_counter_bytes(N));
+  a.stats = a.partial + static_cast<size_t>(N) * stat_slabs * (C / 2);
+  a.stat_slabs = stat_slabs;
   a.y = static_cast<__nv_bfloat16*>(y_bf16_dev);
   a.HW = HW;
   a.C = C;
@@ -243,8 +324,7 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   a.act_silu = act_silu;
   dim3 grid(C / 64, slabs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  k5_gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(a);
-  k5_gn_finalize_kernel<<<dim3(G, N), 256, 0, st>>>(a);
+  k5_gn_stats_kernel<<<dim3(C / 64, stat_slabs, N), GN_THREADS, 0, st>>>(a);
   k5_gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
@@ -269,6 +349,27 @@ extern "C" int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_d
                                 static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x_bf16_dev), static_cast<const uint4*>(h_bf16_dev),
       static_cast<const uint4*>(bias_bf16_dev), static_cast<uint4*>(y_bf16_dev), total8, C / 8);
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
+}
+
+extern "C" int fd_add_layernorm(const void* x_bf16_dev, const void* y_bf16_dev, const void* gamma_bf16_dev,
+                                const void* beta_bf16_dev, void* sum_out_bf16_dev, void* norm_out_bf16_dev,
+                                int64_t M, int C, float eps, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && norm_out_bf16_dev, "fd_add_layernorm: NULL pointer");
+  FD_REQUIRE(M > 0 && (C == 320 || C == 640 || C == 1280), "fd_add_layernorm: need M > 0 and C in {320, 640, 1280}");
+  FD_REQUIRE(!sum_out_bf16_dev || y_bf16_dev, "fd_add_layernorm: sum_out without y");
+  int rc = check_device();
+  if (rc != FD_OK) return rc;
+  const unsigned grid = static_cast<unsigned>((M + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto X = static_cast<const uint32_t*>(x_bf16_dev), Y = static_cast<const uint32_t*>(y_bf16_dev);
+  auto Gm = static_cast<const uint32_t*>(gamma_bf16_dev), Bt = static_cast<const uint32_t*>(beta_bf16_dev);
+  auto So = static_cast<uint32_t*>(sum_out_bf16_dev), No = static_cast<uint32_t*>(norm_out_bf16_dev);
+  if (C == 320) k8_add_layernorm_kernel<5><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
+  else if (C == 640) k8_add_layernorm_kernel<10><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
+  else k8_add_layernorm_kernel<20><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

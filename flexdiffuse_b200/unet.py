@@ -71,6 +71,17 @@ def _gn(x: torch.Tensor, norm: nn.GroupNorm, silu: bool, bias=None) -> torch.Ten
                                  silu, bias)
 
 
+class TembBank:
+    '''All resnets' `time_emb_proj(silu(temb)) + conv1.bias` rows from one GEMM
+    ([B,1280] x [sum C_out,1280]^T) instead of 22 tiny ones per forward.'''
+    def __init__(self, rows: torch.Tensor, slices):
+        self.rows, self.slices = rows, slices
+
+    def take(self, resnet) -> torch.Tensor:
+        a, b = self.slices[id(resnet)]
+        return self.rows[:, a:b]
+
+
 def _conv1x1(x: torch.Tensor, conv: nn.Conv2d) -> torch.Tensor:
     '''1x1 convolution of a channels-last tensor as one cuBLAS GEMM with the bias in its
     epilogue: the NHWC memory *is* the [N*H*W, C] row-major matrix.'''
@@ -106,7 +117,10 @@ class ResnetBlock2D(nn.Module):
         # broadcast kernel, so conv1's bias rides along with the time embedding into norm2 (K5's
         # per-(n,c) bias) and conv2's bias is folded into the residual add (K7).
         h = F.conv2d(_gn(x, self.norm1, silu=True), self.conv1.weight, None, padding=1)
-        tb = F.linear(temb_act, self.time_emb_proj.weight, self._temb_conv1_bias())
+        if isinstance(temb_act, TembBank):
+            tb = temb_act.take(self)   # slice of ONE batched projection for all 22 resnets
+        else:
+            tb = F.linear(temb_act, self.time_emb_proj.weight, self._temb_conv1_bias())
         h = F.conv2d(_gn(h, self.norm2, silu=True, bias=tb), self.conv2.weight, None,
                      padding=1)
         if self.conv_shortcut is not None:
@@ -190,9 +204,15 @@ class BasicTransformerBlock(nn.Module):
         self.norm3 = nn.LayerNorm(dim)
 
     def forward(self, x, kv, ctx_index):
-        x = self.attn1(self.norm1(x)) + x
-        x = self.attn2(self.norm2(x), kv, ctx_index) + x
-        return self.ff(self.norm3(x)) + x
+        # K8: each residual add is fused with the LayerNorm that feeds the next branch
+        ln = _native.add_layernorm
+        if not x.is_contiguous():
+            x = x.contiguous()
+        _, n = ln(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        x, n = ln(x, self.attn1(n), self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        x, n = ln(x, self.attn2(n, kv, ctx_index), self.norm3.weight, self.norm3.bias,
+                  self.norm3.eps)
+        return self.ff(n) + x
 
 
 class SpatialTransformer(nn.Module):
@@ -360,6 +380,16 @@ class UNet2DConditionModel(nn.Module):
             rows += [m.to_k.weight, m.to_v.weight]
             off += 2 * m.dim
         self._kv_weight = torch.cat(rows).to(torch.bfloat16).contiguous()
+        # packed time-embedding projections of every resnet (+ their conv1 bias)
+        resnets = [m for m in self.modules() if isinstance(m, ResnetBlock2D)]
+        self._tb_slices, off = {}, 0
+        for m in resnets:
+            c = m.time_emb_proj.out_features
+            self._tb_slices[id(m)] = (off, off + c)
+            off += c
+        self._tb_weight = torch.cat([m.time_emb_proj.weight for m in resnets]).contiguous()
+        self._tb_bias = torch.cat([m.time_emb_proj.bias + m.conv1.bias
+                                   for m in resnets]).contiguous()
         return self._kv_weight
 
     @torch.no_grad()
@@ -375,6 +405,12 @@ class UNet2DConditionModel(nn.Module):
         ctx[:, :t] = contexts.to(torch.bfloat16)
         kv = _native.kv_project(ctx.view(n_ctx * T_PAD, d), self._kv_weight)
         return KVCache(kv=kv, n_ctx=n_ctx)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._kv_weight = None  # packed K/V and time-embedding weights are stale now
+        self._tb_weight = None
+        return out
 
     def set_attention_slice(self, slice_size):  # flex.py:102; memory knob only
         self._attention_slice = slice_size
@@ -414,6 +450,9 @@ class UNet2DConditionModel(nn.Module):
         emb = self.time_embedding['linear_2'](F.silu(
             self.time_embedding['linear_1'](temb_sin)))
         emb = F.silu(emb)  # every resnet applies silu(temb) first
+        if getattr(self, '_tb_weight', None) is not None and \
+                self._tb_weight.device == emb.device and self._tb_weight.dtype == emb.dtype:
+            emb = TembBank(F.linear(emb, self._tb_weight, self._tb_bias), self._tb_slices)
 
         x = self.conv_in(sample.to(dtype))
         skips = [x]

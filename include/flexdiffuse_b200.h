@@ -185,18 +185,31 @@ int fd_cross_attn(const void* q_bf16_dev,
 int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G); /* size of `workspace_dev` */
 
 int fd_groupnorm_act(const void* x_bf16_dev,     /* [N, HW, C] channels-last activations    */
-                     const void* bias_bf16_dev,  /* [N, C] added before the norm, or NULL   */
+                     const void* bias_bf16_dev,  /* [N, C] rows added before the norm, or NULL */
                      const void* gamma_bf16_dev, /* [C]                                     */
                      const void* beta_bf16_dev,  /* [C]                                     */
-                     void*       workspace_dev,  /* fd_groupnorm_act_workspace_bytes(...)   */
+                     void*       workspace_dev,  /* fd_groupnorm_act_workspace_bytes(...),
+                                                    zero-filled ONCE before its first use    */
                      void*       y_bf16_dev,     /* [N, HW, C]                              */
                      int N, int HW, int C, int G,/* G <= 32, C/G even, C % 64 == 0          */
-                     float eps, int act_silu, void* stream);
+                     float eps, int act_silu,
+                     int64_t bias_row_stride,    /* elements between bias rows (>= C, even) */
+                     void* stream);
 
 /* y = x + h + bias[c]: ResnetBlock2D's residual add with conv2's bias folded in (NHWC bf16). */
 int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev,
                          const void* bias_bf16_dev,  /* [C]                                 */
                          void* y_bf16_dev, int64_t n_elem, int C, void* stream);
+
+/* s = x + y ; n = LayerNorm(s) * gamma + beta   (BasicTransformerBlock: the residual add of one
+ * attention / feed-forward branch fused with the LayerNorm feeding the next one).  y == NULL:
+ * plain LayerNorm of x.  Rows of C in {320, 640, 1280} bf16.                                 */
+int fd_add_layernorm(const void* x_bf16_dev,       /* [M, C]                                  */
+                     const void* y_bf16_dev,       /* [M, C] or NULL                          */
+                     const void* gamma_bf16_dev, const void* beta_bf16_dev,   /* [C]          */
+                     void* sum_out_bf16_dev,       /* [M, C] x + y, or NULL                   */
+                     void* norm_out_bf16_dev,      /* [M, C]                                  */
+                     int64_t M, int C, float eps, void* stream);
 
 /* diffusers GEGLU: out[m, f] = in[m, f] * gelu(in[m, F + f]), exact (erf) GELU.           */
 int fd_geglu(const void* in_bf16_dev,            /* [M, 2F]                                 */

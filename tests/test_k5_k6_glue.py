@@ -75,3 +75,18 @@ def test_groupnorm_is_bit_reproducible(native, cuda_dev):
     a = native.groupnorm_act(x, w, b, 32, 1e-5, True)
     for _ in range(3):
         assert torch.equal(a, native.groupnorm_act(x, w, b, 32, 1e-5, True))
+
+
+@pytest.mark.parametrize('M,C', [(8192, 320), (2048, 640), (133, 1280)])
+@pytest.mark.parametrize('with_y', [True, False])
+def test_add_layernorm_matches_torch(native, cuda_dev, M, C, with_y):
+    g = torch.Generator(device=cuda_dev).manual_seed(M + C)
+    x = (torch.randn(M, C, device=cuda_dev, generator=g) * 2 + 0.3).bfloat16()
+    y = torch.randn(M, C, device=cuda_dev, generator=g).bfloat16() if with_y else None
+    w = (torch.randn(C, device=cuda_dev, generator=g) * 0.3 + 1).bfloat16()
+    b = (torch.randn(C, device=cuda_dev, generator=g) * 0.2).bfloat16()
+    total, norm = native.add_layernorm(x, y, w, b, 1e-5)
+    s = (x.float() + y.float()).bfloat16() if with_y else x
+    assert torch.equal(total, s)
+    ref = F.layer_norm(s.float(), (C,), w.float(), b.float(), 1e-5)
+    torch.testing.assert_close(norm.float(), ref, rtol=1e-2, atol=1e-2)
