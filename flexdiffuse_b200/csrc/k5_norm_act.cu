@@ -168,6 +168,138 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_apply_kernel(const GnArgs a)
   }
 }
 
+// K5 fast path: one thread-block CLUSTER per (sample, group).  Each CTA of the cluster pulls its
+// slab of the group (rows x C/G channels, 20..160 B segments per pixel) into shared memory once,
+// the (sum, sumsq) partials are exchanged through distributed shared memory, and the slab is
+// normalised straight out of shared memory: x is read from L2/HBM exactly once, one launch, no
+// workspace, fixed reduction order.
+struct GnClusterArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* bias;
+  int64_t bias_stride;
+  const __nv_bfloat16* gamma;
+  const __nv_bfloat16* beta;
+  __nv_bfloat16* y;
+  int HW, C, G, rows_per_cta;
+  float eps;
+  int act_silu;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float2 dsmem_ld_f2(const float2* local_ptr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClusterArgs a) {
+  extern __shared__ uint32_t slab[];  // [rows_per_cta][cg2] bf16 pairs
+  __shared__ float2 red[GN_WARPS];
+  __shared__ float2 cta_partial;
+  const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  const int group_id = blockIdx.x / csize;  // (n, g) flattened
+  const int n = group_id / a.G, g = group_id - n * a.G;
+  const int pairs = a.C >> 1, cg2 = (a.C / a.G) >> 1;
+  const int r0 = crank * a.rows_per_cta;
+  const int rows = max(0, min(a.HW, r0 + a.rows_per_cta) - r0);
+  const int items = rows * cg2;
+  const size_t gbase = (static_cast<size_t>(n) * a.HW + r0) * pairs + static_cast<size_t>(g) * cg2;
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + gbase;
+  const uint32_t* bb =
+      a.bias ? reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride) + g * cg2 : nullptr;
+
+  float s = 0.f, q = 0.f;
+  for (int i0 = threadIdx.x; i0 < items; i0 += 4 * GN_THREADS) {
+    uint32_t v[4];
+    int jj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * GN_THREADS;
+      if (i < items) {
+        const int r = i / cg2;
+        jj[u] = i - r * cg2;
+        v[u] = xb[static_cast<size_t>(r) * pairs + jj[u]];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * GN_THREADS;
+      if (i < items) {
+        slab[i] = v[u];
+        float2 f = bf2_to_f2(v[u]);
+        if (bb) {
+          const float2 b = bf2_to_f2(bb[jj[u]]);
+          f.x += b.x;
+          f.y += b.y;
+        }
+        s += f.x + f.y;
+        q += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  // block reduction in a fixed order
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_float2(s, q);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float2 t = red[0];
+#pragma unroll
+    for (int w = 1; w < GN_WARPS; ++w) {
+      t.x += red[w].x;
+      t.y += red[w].y;
+    }
+    cta_partial = t;
+  }
+  cluster_sync_all();  // every CTA's partial is visible cluster-wide
+  float ts = 0.f, tq = 0.f;
+  for (uint32_t r = 0; r < csize; ++r) {  // same order on every CTA => identical statistics
+    const float2 t = dsmem_ld_f2(&cta_partial, r);
+    ts += t.x;
+    tq += t.y;
+  }
+  cluster_sync_all();  // nobody exits (or reuses smem) while peers still read its partial
+  const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
+  const float mean = ts / cnt;
+  const float rstd = rsqrtf(fmaxf(tq / cnt - mean * mean, 0.f) + a.eps);
+
+  uint32_t* yb = reinterpret_cast<uint32_t*>(a.y) + gbase;
+  const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.gamma) + g * cg2;
+  const uint32_t* tb = reinterpret_cast<const uint32_t*>(a.beta) + g * cg2;
+  for (int i = threadIdx.x; i < items; i += GN_THREADS) {
+    const int r = i / cg2, j = i - r * cg2;
+    const float2 f = bf2_to_f2(slab[i]);
+    const float2 gam = bf2_to_f2(gb[j]), bet = bf2_to_f2(tb[j]);
+    float2 b = make_float2(0.f, 0.f);
+    if (bb) b = bf2_to_f2(bb[j]);
+    float ox = (f.x + b.x - mean) * rstd * gam.x + bet.x;
+    float oy = (f.y + b.y - mean) * rstd * gam.y + bet.y;
+    if (a.act_silu) {
+      ox = ox / (1.0f + __expf(-ox));
+      oy = oy / (1.0f + __expf(-oy));
+    }
+    __nv_bfloat162 o = __floats2bfloat162_rn(ox, oy);
+    yb[static_cast<size_t>(r) * pairs + j] = *reinterpret_cast<uint32_t*>(&o);
+  }
+}
+
 // K7: y = x + h + bias[c]   (residual add with the convolution bias folded in), NHWC bf16
 __global__ void __launch_bounds__(256) k7_add_bias_residual_kernel(const uint4* __restrict__ x,
                                                                    const uint4* __restrict__ h,
@@ -322,8 +454,43 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   a.slabs = slabs;
   a.eps = eps;
   a.act_silu = act_silu;
-  dim3 grid(C / 64, slabs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    // fast path: the whole group fits the shared memory of a cluster of <= 8 CTAs
+    const int64_t group_bytes = static_cast<int64_t>(HW) * (C / G) * 2;
+    int cl = 1;
+    while (cl < 8 && (group_bytes / cl > 48 * 1024 || static_cast<int64_t>(N) * G * cl < 2 * sm_count())) cl *= 2;
+    while (cl > 1 && HW < cl * 8) cl /= 2;
+    const int rows_per_cta = (HW + cl - 1) / cl;
+    const int64_t smem = static_cast<int64_t>(rows_per_cta) * (C / G) * 2;
+    if (smem <= 96 * 1024 && static_cast<int64_t>(N) * G * cl <= 0x7fffffff) {
+      GnClusterArgs c;
+      c.x = a.x; c.bias = a.bias; c.bias_stride = a.bias_stride; c.gamma = a.gamma; c.beta = a.beta; c.y = a.y;
+      c.HW = HW; c.C = C; c.G = G; c.rows_per_cta = rows_per_cta; c.eps = eps; c.act_silu = act_silu;
+      static thread_local int attr_device = -1;
+      int dev = 0;
+      FD_CUDA_OK(cudaGetDevice(&dev));
+      if (attr_device != dev) {
+        FD_CUDA_OK(cudaFuncSetAttribute(k5_gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr_device = dev;
+      }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(static_cast<unsigned>(N * G * cl));
+      cfg.blockDim = dim3(GN_THREADS);
+      cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = cl;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k5_gn_cluster_kernel, c));
+      return FD_OK;
+    }
+  }
+  dim3 grid(C / 64, slabs, N);
   k5_gn_stats_kernel<<<dim3(C / 64, stat_slabs, N), GN_THREADS, 0, st>>>(a);
   k5_gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(a);
   FD_CUDA_OK(cudaGetLastError());
