@@ -26,6 +26,7 @@ constexpr int GN_WARPS = GN_THREADS / 32;
 constexpr int GN_ROWS = 32;        // rows (pixels) per CTA in the apply phase
 constexpr int GN_STAT_ROWS = 128;  // rows per CTA in the statistics phase
 constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_MAX_CG2 = 64;     // channel pairs per group on the cluster path (C/G <= 128)
 
 struct GnArgs {
   const __nv_bfloat16* x;      // [N, HW, C] (channels_last view of [N, C, H, W])
@@ -222,12 +223,21 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
   const uint32_t* bb =
       a.bias ? reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride) + g * cg2 : nullptr;
 
+  // per-pair constants of this group: (scale, shift) are finished once mean / rstd are known
+  __shared__ float2 s_gam[GN_MAX_CG2], s_bet[GN_MAX_CG2], s_bias[GN_MAX_CG2];
+  if (threadIdx.x < cg2) {
+    s_gam[threadIdx.x] = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.gamma)[g * cg2 + threadIdx.x]);
+    s_bet[threadIdx.x] = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.beta)[g * cg2 + threadIdx.x]);
+    s_bias[threadIdx.x] = bb ? bf2_to_f2(bb[threadIdx.x]) : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
   float s = 0.f, q = 0.f;
-  for (int i0 = threadIdx.x; i0 < items; i0 += 4 * GN_THREADS) {
-    uint32_t v[4];
-    int jj[4];
+  constexpr int UNR = 8;  // loads in flight per thread
+  for (int i0 = threadIdx.x; i0 < items; i0 += UNR * GN_THREADS) {
+    uint32_t v[UNR];
+    int jj[UNR];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int i = i0 + u * GN_THREADS;
       if (i < items) {
         const int r = i / cg2;
@@ -236,16 +246,14 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < UNR; ++u) {
       const int i = i0 + u * GN_THREADS;
       if (i < items) {
         slab[i] = v[u];
         float2 f = bf2_to_f2(v[u]);
-        if (bb) {
-          const float2 b = bf2_to_f2(bb[jj[u]]);
-          f.x += b.x;
-          f.y += b.y;
-        }
+        const float2 b = s_bias[jj[u]];
+        f.x += b.x;
+        f.y += b.y;
         s += f.x + f.y;
         q += f.x * f.x + f.y * f.y;
       }
@@ -275,20 +283,15 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
     ts += t.x;
     tq += t.y;
   }
-  cluster_sync_all();  // nobody exits (or reuses smem) while peers still read its partial
   const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
   const float mean = ts / cnt;
   const float rstd = rsqrtf(fmaxf(tq / cnt - mean * mean, 0.f) + a.eps);
 
   uint32_t* yb = reinterpret_cast<uint32_t*>(a.y) + gbase;
-  const uint32_t* gb = reinterpret_cast<const uint32_t*>(a.gamma) + g * cg2;
-  const uint32_t* tb = reinterpret_cast<const uint32_t*>(a.beta) + g * cg2;
   for (int i = threadIdx.x; i < items; i += GN_THREADS) {
     const int r = i / cg2, j = i - r * cg2;
     const float2 f = bf2_to_f2(slab[i]);
-    const float2 gam = bf2_to_f2(gb[j]), bet = bf2_to_f2(tb[j]);
-    float2 b = make_float2(0.f, 0.f);
-    if (bb) b = bf2_to_f2(bb[j]);
+    const float2 gam = s_gam[j], bet = s_bet[j], b = s_bias[j];
     float ox = (f.x + b.x - mean) * rstd * gam.x + bet.x;
     float oy = (f.y + b.y - mean) * rstd * gam.y + bet.y;
     if (a.act_silu) {
@@ -298,6 +301,7 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
     __nv_bfloat162 o = __floats2bfloat162_rn(ox, oy);
     yb[static_cast<size_t>(r) * pairs + j] = *reinterpret_cast<uint32_t*>(&o);
   }
+  cluster_sync_all();  // nobody exits while a peer may still be reading its partial
 }
 
 // K7: y = x + h + bias[c]   (residual add with the convolution bias folded in), NHWC bf16
@@ -463,7 +467,7 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
     while (cl > 1 && HW < cl * 8) cl /= 2;
     const int rows_per_cta = (HW + cl - 1) / cl;
     const int64_t smem = static_cast<int64_t>(rows_per_cta) * (C / G) * 2;
-    if (smem <= 96 * 1024 && static_cast<int64_t>(N) * G * cl <= 0x7fffffff) {
+    if (smem <= 96 * 1024 && C / G <= 2 * GN_MAX_CG2 && static_cast<int64_t>(N) * G * cl <= 0x7fffffff) {
       GnClusterArgs c;
       c.x = a.x; c.bias = a.bias; c.bias_stride = a.bias_stride; c.gamma = a.gamma; c.beta = a.beta; c.y = a.y;
       c.HW = HW; c.C = C; c.G = G; c.rows_per_cta = rows_per_cta; c.eps = eps; c.act_silu = act_silu;

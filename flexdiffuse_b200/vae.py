@@ -1,8 +1,8 @@
 '''SD-v1 `AutoencoderKL` (diffusers 0.3.0), the `vae` the reference pipeline decodes
 with at /root/reference/pipeline/flex.py:112-124 and encodes the init image with at
-flex.py:189-192.  Pure PyTorch (cuDNN convolutions) -- BASELINE.json's north_star keeps
-the VAE out of the hand-written kernels; it sits either side of the hot loop
-(SURVEY 8f rank 4).  Parameter names follow diffusers so a `state_dict` is shared
+flex.py:189-192.  Convolutions and the mid-block attention stay in PyTorch (cuDNN / SDPA) --
+BASELINE.json's north_star keeps the VAE out of the four hand-written subsystems; it sits
+either side of the hot loop.  Its GroupNorm+SiLU pairs go through K5.  Parameter names follow diffusers so a `state_dict` is shared
 with the oracle restatement.
 '''
 from __future__ import annotations
@@ -13,6 +13,14 @@ from typing import Optional
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import _native
+
+
+def _gn(x: torch.Tensor, norm: nn.GroupNorm, silu: bool) -> torch.Tensor:
+    '''GroupNorm (+ SiLU) through K5 (`fd_groupnorm_act`).  CUDA bf16 only, like the UNet: there
+    is no PyTorch / CPU fallback (the native call raises).'''
+    return _native.groupnorm_act(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu)
 
 
 class VaeResnet(nn.Module):
@@ -25,8 +33,8 @@ class VaeResnet(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x):
-        h = self.conv1(F.silu(self.norm1(x)))
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv1(_gn(x, self.norm1, True))
+        h = self.conv2(_gn(h, self.norm2, True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -44,10 +52,10 @@ class AttentionBlock(nn.Module):
 
     def forward(self, x):
         B, C, H, W = x.shape
-        h = self.group_norm(x).view(B, C, H * W).transpose(1, 2)
+        h = _gn(x, self.group_norm, False).permute(0, 2, 3, 1).reshape(B, H * W, C)
         q, k, v = self.query(h), self.key(h), self.value(h)
         o = F.scaled_dot_product_attention(q[:, None], k[:, None], v[:, None])[:, 0]
-        o = self.proj_attn(o).transpose(1, 2).reshape(B, C, H, W)
+        o = self.proj_attn(o).reshape(B, H, W, C).permute(0, 3, 1, 2)
         return o + x
 
 
@@ -124,7 +132,7 @@ class Encoder(nn.Module):
         for b in self.down_blocks:
             x = b(x)
         x = self.mid_block(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(_gn(x, self.conv_norm_out, True))
 
 
 class Decoder(nn.Module):
@@ -145,7 +153,7 @@ class Decoder(nn.Module):
         x = self.mid_block(self.conv_in(z))
         for b in self.up_blocks:
             x = b(x)
-        return self.conv_out(F.silu(self.conv_norm_out(x)))
+        return self.conv_out(_gn(x, self.conv_norm_out, True))
 
 
 class DiagonalGaussianDistribution:
