@@ -24,6 +24,7 @@ FD_BLEND_ZERO_DIVISION = 1
 # every symbol include/flexdiffuse_b200.h declares (tests check they all export)
 ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
+               'fd_sim_blend_workspace_bytes',
                'fd_kv_project', 'fd_cross_attn',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu')
@@ -83,9 +84,11 @@ def lib() -> C.CDLL:
     l.fd_cfg_sched_step.restype = C.c_int
     l.fd_sim_blend.argtypes = [
         vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
-        vp, vp, vp, vp, vp, vp, vp
+        vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp
     ]
     l.fd_sim_blend.restype = C.c_int
+    l.fd_sim_blend_workspace_bytes.argtypes = [C.c_int] * 3
+    l.fd_sim_blend_workspace_bytes.restype = C.c_int64
     l.fd_kv_project.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     l.fd_kv_project.restype = C.c_int
     l.fd_cross_attn.argtypes = [
@@ -236,11 +239,14 @@ def sim_blend(text: torch.Tensor,
     arr = (TweenParams * P)(*params)
     params_dev = torch.frombuffer(bytearray(bytes(arr)),
                                   dtype=torch.uint8).to(dev)
+    ws_bytes = lib().fd_sim_blend_workspace_bytes(G, A, D)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     rc = lib().fd_sim_blend(ptr(text), ptr(guide), B, G, T, A, D,
                             ptr(params_dev),
                             ptr(linear_weights), P, ptr(out), ptr(map_s),
                             ptr(map_idx), ptr(weights), ptr(status), ptr(sim),
-                            stream_ptr(dev))
+                            ptr(ws), ws_bytes, stream_ptr(dev))
+    count_launch()  # guide prep kernel
     check(rc, 'fd_sim_blend')
     count_launch()
     return dict(out=out, map_s=map_s, map_idx=map_idx, weights=weights,

@@ -8,12 +8,16 @@
 //   guidance.py:215-272  Tweener.tween
 // Algorithm spec: SURVEY.md 3.6 (verified bit-level against the reference by the oracle tests).
 //
-// Structure of one CTA (384 threads, 1 CTA / SM):
+// A tiny prep kernel splits the (usually shared) guide once into tf32 hi / lo planes and its inverse
+// L2 norms.  Structure of one CTA of the main kernel (384 threads, 1 CTA / SM):
 //   1. GEMM  D[i,j] = <guide_i, text_j>  (A<=384 x T<=80 x D) on tcgen05, kind::tf32 with the
 //      3-pass hi/lo split (hi*hi + lo*hi + hi*lo) so the logits are fp32-equivalent
 //      (a single bf16/tf32 pass flips arg-max / threshold decisions).
-//      Operands go global -> registers (split + sum of squares for the L2 norms) -> shared memory
-//      in the K-major SWIZZLE_128B UMMA layout; next chunk's global loads overlap the MMAs.
+//      Warp-specialised 2-stage pipeline over K chunks of 32: warp 0 TMA-loads the guide hi / lo
+//      tiles (SWIZZLE_128B), warps 2-11 split the prompt's own chunk in registers into the same
+//      layout (+ sum of squares for its L2 norms), warp 1 issues the MMAs.  Guide rows beyond the
+//      last full 128-row tile (the 257th CLIP token) are <= 8 dot products per text token and go
+//      to the CUDA cores instead of wasting a third MMA tile.
 //      Accumulators: up to 3 tiles of 128 lanes x 80 columns in TMEM.
 //   2. Softmax over the text tokens: one thread per TMEM lane (= guide token), no shuffles.
 //      P^T is parked in shared memory (aliasing the operand staging area).
@@ -34,17 +38,34 @@ constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
 constexpr int KC = 32;            // fp32 per K chunk (one 128 B swizzle row)
 constexpr int A_TILE_BYTES = 128 * 128;
 constexpr int B_TILE_BYTES = NPAD * 128;
-constexpr int STAGE_BYTES = 2 * MAX_TILES * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 118,784
+constexpr int STAGE_BYTES = 2 * MAX_TILES * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 118,784 (3 tiles)
+constexpr int MAX_REM = 8;        // guide rows past the last full tile that go to the CUDA cores
+constexpr int TEXT_WARPS = K1_WARPS - 2;
+constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 320
 constexpr int PT_STRIDE = MAX_TILES * 128;                                   // floats per P^T row
 constexpr int MAXT = 80;
-constexpr int A_ITEMS = (MAX_TILES * 128 * 8 + K1_THREADS - 1) / K1_THREADS;  // 8
-constexpr int B_ITEMS = (NPAD * 8 + K1_THREADS - 1) / K1_THREADS;            // 2
+constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 2
 
 static_assert((MAXT - 1) * PT_STRIDE * 4 <= STAGE_BYTES + 8192, "P^T must fit the staging area");
 
+// development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
+static long long* g_k1_timing = nullptr;
+__device__ __forceinline__ long long k1_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define K1_STAMP(slot)                                                                   \
+  do {                                                                                   \
+    if (a.timing && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) a.timing[slot] = k1_gtime(); \
+  } while (0)
+
 struct K1Args {
+  long long* timing;
   const float* text;     // [n_text, T, D]
   const float* guide;    // [guide_batch, A, D]
+  const float* inv_norm_a;  // [guide_batch, A] from the prep kernel
+  int n_mma_tiles, n_stages;
   int n_text, guide_batch, T, A, D;
   const fd_tween_params* params;  // device [n_params]
   const float* lin_w;             // device [n_params, T]
@@ -69,12 +90,15 @@ struct K1Smem {
   unsigned int used[MAX_TILES * 128 / 32];  // bitmask of guide tokens already consumed
   float iw[MAXT + 16];
   int sel[MAXT + 16];
+  float rem[MAX_REM][NPAD];  // raw dot products of the remainder guide rows
   int pick_r, pick_i, flag;
-  uint64_t mma_bar;
+  uint64_t full_bar[2], empty_bar[2], done_bar;
   uint32_t tmem_slot;
 };
 
-constexpr int K1_SMEM_BYTES = 1024 + STAGE_BYTES + 8192 + sizeof(K1Smem);
+constexpr int K1_STAGE_AREA = 2 * (2 * 2 * A_TILE_BYTES + 2 * B_TILE_BYTES);  // 172,032: two 2-tile stages
+static_assert(K1_STAGE_AREA >= STAGE_BYTES + 8192, "stage area must also hold one 3-tile stage and P^T");
+constexpr int K1_SMEM_BYTES = 1024 + K1_STAGE_AREA + sizeof(K1Smem);
 
 __device__ __forceinline__ void argmax_combine(float& s, int& i, float os, int oi) {
   // larger s wins, ties -> lower index; index < 0 means "nothing"
@@ -123,16 +147,45 @@ __device__ __forceinline__ int warp_consume_all_unused(unsigned int* used, int A
   return hi;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Args a) {
+// guide fp32 -> tf32 hi plane, lo plane (x - hi, exact in fp32) and 1 / |row|.  One warp per row.
+__global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, float* __restrict__ hi,
+                                                            float* __restrict__ lo, float* __restrict__ inv_norm,
+                                                            int rows, int D) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float ss = 0.f;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(g + static_cast<size_t>(row) * D + c);
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    l.x = v.x - h.x;
+    l.y = v.y - h.y;
+    l.z = v.z - h.z;
+    l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + static_cast<size_t>(row) * D + c) = h;
+    *reinterpret_cast<float4*>(lo + static_cast<size_t>(row) * D + c) = l;
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) inv_norm[row] = 1.0f / sqrtf(ss);
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const K1Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  uint8_t* a_hi = stage;
-  uint8_t* a_lo = stage + MAX_TILES * A_TILE_BYTES;
-  uint8_t* b_hi = stage + 2 * MAX_TILES * A_TILE_BYTES;
-  uint8_t* b_lo = b_hi + B_TILE_BYTES;
+  // stage s: [hi tiles][lo tiles][text hi][text lo]
+  const int n_mma = a.n_mma_tiles;
+  const uint32_t stage_bytes = 2u * n_mma * A_TILE_BYTES + 2u * B_TILE_BYTES;
   float* pt = reinterpret_cast<float*>(stage);  // aliases the staging area after the GEMM
-  K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + STAGE_BYTES + 8192);
+  K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + K1_STAGE_AREA);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -145,7 +198,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
   const uint32_t tmem_cols = 256;  // 3 x 80 = 240 -> next power of two
 
   if (tid == 0) {
-    mbar_init(&sm.mma_bar, 1);
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&sm.full_bar[st], 1 + TEXT_WARPS);  // TMA expect_tx arrive + one arrive per text warp
+      mbar_init(&sm.empty_bar[st], 1);
+    }
+    mbar_init(&sm.done_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -156,116 +215,146 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm.tmem_slot;
+  K1_STAMP(0);
 
   // ------------------------------------------------------------------ 1. GEMM
-  const int a_items_total = A * 8;  // float4 items per chunk (row, 16 B column)
-  const int b_items_total = T * 8;
-  float4 ra[A_ITEMS], rb[B_ITEMS];
-  float ssa[A_ITEMS], ssb[B_ITEMS];
-#pragma unroll
-  for (int j = 0; j < A_ITEMS; ++j) ssa[j] = 0.f;
-#pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
-
-  auto load_chunk = [&](int kc) {
-#pragma unroll
-    for (int j = 0; j < A_ITEMS; ++j) {
-      const int f = tid + j * K1_THREADS;
-      if (f < a_items_total)
-        ra[j] = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
-      else
-        ra[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int f = tid + j * K1_THREADS;
-      if (f < b_items_total)
-        rb[j] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
-      else
-        rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  auto split_store = [&](const float4& v, uint8_t* hi_base, uint8_t* lo_base, int f) {
-    const uint32_t row = f >> 3, c16 = f & 7;
-    const uint32_t tile = row >> 7, r = row & 127;
-    const uint32_t off = tile * A_TILE_BYTES + sw128_offset(r, c16);
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    l.x = v.x - h.x;
-    l.y = v.y - h.y;
-    l.z = v.z - h.z;
-    l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi_base + off) = h;
-    *reinterpret_cast<float4*>(lo_base + off) = l;
-  };
-
   const int num_kc = D / KC;
-  const uint32_t idesc = umma_idesc(UMMA_TF32, 128, NPAD, 0, 0);
-  load_chunk(0);
-  for (int kc = 0; kc < num_kc; ++kc) {
-    if (kc > 0) mbar_wait(&sm.mma_bar, (kc - 1) & 1);  // MMAs of the previous chunk retired
-#pragma unroll
-    for (int j = 0; j < A_ITEMS; ++j) {
-      const int f = tid + j * K1_THREADS;
-      if (f < n_tiles * 128 * 8) {  // pad rows are written as zeros
-        split_store(ra[j], a_hi, a_lo, f);
-        ssa[j] += ra[j].x * ra[j].x + ra[j].y * ra[j].y + ra[j].z * ra[j].z + ra[j].w * ra[j].w;
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      const int f = tid + j * K1_THREADS;
-      if (f < NPAD * 8) {
-        split_store(rb[j], b_hi, b_lo, f);  // tile index is always 0 for f < 128*8
-        ssb[j] += rb[j].x * rb[j].x + rb[j].y * rb[j].y + rb[j].z * rb[j].z + rb[j].w * rb[j].w;
-      }
-    }
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      for (int t = 0; t < n_tiles; ++t) {
-        const uint64_t ah = umma_desc_sw128(smem_u32(a_hi + t * A_TILE_BYTES), 16, 1024);
-        const uint64_t al = umma_desc_sw128(smem_u32(a_lo + t * A_TILE_BYTES), 16, 1024);
-        const uint64_t bh = umma_desc_sw128(smem_u32(b_hi), 16, 1024);
-        const uint64_t bl = umma_desc_sw128(smem_u32(b_lo), 16, 1024);
-        const uint32_t d = tmem_base + t * NPAD;
-#pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
-          mma_tf32_ss(d, al + 2 * ks, bh + 2 * ks, idesc, (kc | ks) != 0);  // small terms first
-          mma_tf32_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
-          mma_tf32_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, 1);
+  const int nst = a.n_stages;
+  const int g_idx = a.guide_batch == 1 ? 0 : b_idx;
+  if (warp == 0) {
+    // ---- TMA producer: guide hi / lo tiles of every K chunk
+    if (elect_one()) {
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int st = kc % nst;
+        const uint32_t ph = (kc / nst) & 1;
+        mbar_wait_backoff(&sm.empty_bar[st], ph ^ 1);
+        mbar_expect_tx(&sm.full_bar[st], 2u * n_mma * A_TILE_BYTES);
+        uint8_t* base = stage + st * stage_bytes;
+        for (int t = 0; t < n_mma; ++t) {
+          tma_load_3d(base + t * A_TILE_BYTES, &tm_hi, &sm.full_bar[st], kc * KC, t * 128, g_idx);
+          tma_load_3d(base + (n_mma + t) * A_TILE_BYTES, &tm_lo, &sm.full_bar[st], kc * KC, t * 128, g_idx);
         }
       }
-      tc_commit(&sm.mma_bar);
     }
-    if (kc + 1 < num_kc) load_chunk(kc + 1);  // overlaps the MMAs just issued
-  }
-  // L2 norms: the 8 lanes that share a row sit in one aligned group of 8 lanes
+  } else if (warp == 1) {
+    // ---- MMA issuer
+    if (elect_one()) {
+      const uint32_t idesc = umma_idesc(UMMA_TF32, 128, NPAD, 0, 0);
+      for (int kc = 0; kc < num_kc; ++kc) {
+        const int st = kc % nst;
+        mbar_wait_backoff(&sm.full_bar[st], (kc / nst) & 1);
+        tc_fence_after();
+        uint8_t* base = stage + st * stage_bytes;
+        const uint64_t bh = umma_desc_sw128(smem_u32(base + 2 * n_mma * A_TILE_BYTES), 16, 1024);
+        const uint64_t bl = umma_desc_sw128(smem_u32(base + 2 * n_mma * A_TILE_BYTES + B_TILE_BYTES), 16, 1024);
+        for (int t = 0; t < n_mma; ++t) {
+          const uint64_t ah = umma_desc_sw128(smem_u32(base + t * A_TILE_BYTES), 16, 1024);
+          const uint64_t al = umma_desc_sw128(smem_u32(base + (n_mma + t) * A_TILE_BYTES), 16, 1024);
+          const uint32_t d = tmem_base + t * NPAD;
 #pragma unroll
-  for (int j = 0; j < A_ITEMS; ++j) {
-    float s = ssa[j];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const int f = tid + j * K1_THREADS;
-    if ((f & 7) == 0 && (f >> 3) < MAX_TILES * 128) sm.inv_norm_a[f >> 3] = 1.0f / sqrtf(s);
-  }
+          for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
+            mma_tf32_ss(d, al + 2 * ks, bh + 2 * ks, idesc, (kc | ks) != 0);  // small terms first
+            mma_tf32_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
+            mma_tf32_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, 1);
+          }
+        }
+        tc_commit(&sm.empty_bar[st]);
+      }
+      tc_commit(&sm.done_bar);
+    }
+  } else {
+    // ---- text warps: this prompt's chunk -> registers -> hi / lo split -> swizzled smem
+    const int tt = tid - 64;
+    float4 rb[B_ITEMS];
+    float ssb[B_ITEMS];
 #pragma unroll
-  for (int j = 0; j < B_ITEMS; ++j) {
-    float s = ssb[j];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    const int f = tid + j * K1_THREADS;
-    if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(s);
+    for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
+    auto load_chunk = [&](int kc) {
+#pragma unroll
+      for (int j = 0; j < B_ITEMS; ++j) {
+        const int f = tt + j * TEXT_THREADS;
+        if (f < T * 8)
+          rb[j] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
+        else
+          rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    load_chunk(0);
+    for (int kc = 0; kc < num_kc; ++kc) {
+      const int st = kc % nst;
+      mbar_wait(&sm.empty_bar[st], ((kc / nst) & 1) ^ 1);
+      uint8_t* b_hi = stage + st * stage_bytes + 2 * n_mma * A_TILE_BYTES;
+      uint8_t* b_lo = b_hi + B_TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < B_ITEMS; ++j) {
+        const int f = tt + j * TEXT_THREADS;
+        if (f < NPAD * 8) {  // rows T..79 are written as zeros
+          const float4 v = rb[j];
+          const uint32_t off = sw128_offset(f >> 3, f & 7);
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = v.x - h.x;
+          l.y = v.y - h.y;
+          l.z = v.z - h.z;
+          l.w = v.w - h.w;
+          *reinterpret_cast<float4*>(b_hi + off) = h;
+          *reinterpret_cast<float4*>(b_lo + off) = l;
+          ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full_bar[st]);
+      if (kc + 1 < num_kc) load_chunk(kc + 1);  // in flight while the MMAs of this chunk run
+    }
+    // L2 norms of the text rows: the 8 threads that share a row sit in one aligned group of 8 lanes
+#pragma unroll
+    for (int j = 0; j < B_ITEMS; ++j) {
+      float ss = ssb[j];
+      ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      const int f = tt + j * TEXT_THREADS;
+      if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
+    }
+    // remainder guide rows (A - 128 * n_mma <= 8) on the CUDA cores, exact fp32: warp w takes
+    // text tokens w, w + 10, ...
+    const int rem0 = n_mma * 128;
+    const int n_rem = A - rem0;
+    if (n_rem > 0) {
+      const float* gr = a.guide + (static_cast<size_t>(g_idx) * A + rem0) * D;
+      for (int j = warp - 2; j < T; j += TEXT_WARPS) {
+        float acc[MAX_REM];
+#pragma unroll
+        for (int r = 0; r < MAX_REM; ++r) acc[r] = 0.f;
+        for (int c = lane * 4; c < D; c += 128) {
+          const float4 tv = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(j) * D + c));
+#pragma unroll
+          for (int r = 0; r < MAX_REM; ++r) {
+            if (r < n_rem) {
+              const float4 gv = __ldg(reinterpret_cast<const float4*>(gr + static_cast<size_t>(r) * D + c));
+              acc[r] += tv.x * gv.x + tv.y * gv.y + tv.z * gv.z + tv.w * gv.w;
+            }
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < MAX_REM; ++r) {
+          float v = acc[r];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == 0 && r < n_rem) sm.rem[r][j] = v;
+        }
+      }
+    }
   }
-  mbar_wait(&sm.mma_bar, (num_kc - 1) & 1);
+  for (int i = tid; i < A; i += K1_THREADS) sm.inv_norm_a[i] = a.inv_norm_a[static_cast<size_t>(g_idx) * A + i];
+  mbar_wait(&sm.done_bar, 0);
   tc_fence_after();
-  __syncthreads();  // norms visible; staging area free for P^T
+  __syncthreads();  // norms + remainder rows visible; staging area free for P^T
+  K1_STAMP(1);
 
   // ------------------------------------------------------------------ 2. softmax per lane
   {
@@ -273,34 +362,44 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
     if (tile < n_tiles) {
       const int i = tile * 128 + quarter * 32 + lane;
       float l[NPAD];
+      if (tile < n_mma) {
+        uint32_t v[NPAD / 16][16];
 #pragma unroll
-      for (int c = 0; c < NPAD; c += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * NPAD + c, v);
+        for (int c = 0; c < NPAD / 16; ++c)
+          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * NPAD + 16 * c, v[c]);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 16; ++q) l[c + q] = __uint_as_float(v[q]);
+        for (int c = 0; c < NPAD / 16; ++c)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) l[16 * c + q] = __uint_as_float(v[c][q]);
+      } else {
+        const int r = min(max(i - n_mma * 128, 0), MAX_REM - 1);
+#pragma unroll
+        for (int j = 0; j < NPAD; ++j) l[j] = sm.rem[r][j];
       }
       if (i < A) {
-        const float ia = sm.inv_norm_a[i];
+        // logits 100 * cos(guide_i, text_j) (guidance.py:43-50) in the log2 domain
+        const float ia = sm.inv_norm_a[i] * (100.0f * 1.4426950408889634f);
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < NPAD; ++j) {
-          // 100 * cos(guide_i, text_j)   (guidance.py:43-50)
-          l[j] = (j < T) ? 100.0f * (l[j] * ia * sm.inv_norm_b[j]) : -INFINITY;
+          l[j] = (j < T) ? l[j] * ia * sm.inv_norm_b[j] : -INFINITY;
           mx = fmaxf(mx, l[j]);
         }
-        float sum = 0.f;
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < NPAD; ++j) {
-          l[j] = (j < T) ? expf(l[j] - mx) : 0.f;
-          sum += l[j];
+        for (int j = 0; j < NPAD; j += 2) {
+          l[j] = ex2_approx(l[j] - mx);  // padded columns: 2^-inf = 0
+          l[j + 1] = ex2_approx(l[j + 1] - mx);
+          s0 += l[j];
+          s1 += l[j + 1];
         }
+        const float inv = 1.0f / (s0 + s1);
         float* simrow = (a.sim && blockIdx.y == 0) ? a.sim + (static_cast<size_t>(b_idx) * A + i) * T : nullptr;
 #pragma unroll
         for (int j = 0; j < NPAD; ++j) {
           if (j < T) {
-            const float p = l[j] / sum;
+            const float p = l[j] * inv;
             if (j >= 1) pt[(j - 1) * PT_STRIDE + i] = p;  // header column dropped (guidance.py:55)
             if (simrow) simrow[j] = p;
           }
@@ -311,6 +410,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
   }
   __syncthreads();
 
+  K1_STAMP(2);
   // ------------------------------------------------------------------ 3..5 per parameter set
   const int p_begin = blockIdx.y * a.params_per_cta;
   const int p_end = min(a.n_params, p_begin + a.params_per_cta);
@@ -459,6 +559,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
       __syncthreads();
     }
 
+    if (p == p_begin) K1_STAMP(3);
     // ---------------- 4. weights: one warp, token r = lane + 32 k
     if (warp == 0) {
       constexpr int KR = 3;  // 96 >= MAXT tokens
@@ -612,6 +713,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
     }
     __syncthreads();
 
+    if (p == p_begin) K1_STAMP(4);
     // ---------------- 5. select / lerp, 2 rows of 192 float4 per pass
     {
       const int d4 = D / 4;
@@ -640,6 +742,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
     __syncthreads();
   }
 
+  K1_STAMP(5);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -651,10 +754,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_sim_blend_kernel(const K1Arg
 }  // namespace
 }  // namespace fd
 
+extern "C" int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D) {
+  return (2 * static_cast<int64_t>(guide_batch) * A * D + static_cast<int64_t>(guide_batch) * A) * 4 + 64;
+}
+
+// development aid (not part of the product ABI): device buffer of >= 8 int64 for phase timestamps
+extern "C" void fd_debug_set_k1_timing(void* buf_dev) { fd::g_k1_timing = static_cast<long long*>(buf_dev); }
+
 extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n_text, int guide_batch, int T, int A,
                             int D, const fd_tween_params* params_dev, const float* linear_weights_dev, int n_params,
                             float* out_dev, float* map_s_dev, int32_t* map_idx_dev, float* weights_dev,
-                            int32_t* status_dev, float* sim_dev, void* stream) {
+                            int32_t* status_dev, float* sim_dev, void* workspace_dev, int64_t workspace_bytes,
+                            void* stream) {
   using namespace fd;
   FD_REQUIRE(text_dev && guide_dev && params_dev && linear_weights_dev && out_dev, "fd_sim_blend: NULL pointer");
   FD_REQUIRE(n_text > 0 && n_params > 0, "fd_sim_blend: n_text=%d n_params=%d must be positive", n_text, n_params);
@@ -669,7 +780,35 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   int rc = check_device();
   if (rc != FD_OK) return rc;
 
+  // workspace: [guide hi plane][guide lo plane][inverse norms]
+  const int64_t plane = static_cast<int64_t>(guide_batch) * A * D;
+  FD_REQUIRE(workspace_dev && workspace_bytes >= fd_sim_blend_workspace_bytes(guide_batch, A, D),
+             "fd_sim_blend: workspace too small (need fd_sim_blend_workspace_bytes)");
+  FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0, "fd_sim_blend: workspace must be 16-byte aligned");
+  float* g_hi = static_cast<float*>(workspace_dev);
+  float* g_lo = g_hi + plane;
+  float* g_inv = g_lo + plane;
+  cudaStream_t cst = static_cast<cudaStream_t>(stream);
+  {
+    const int rows = guide_batch * A;
+    k1_prep_guide_kernel<<<(rows + 7) / 8, 256, 0, cst>>>(guide_dev, g_hi, g_lo, g_inv, rows, D);
+    FD_CUDA_OK(cudaGetLastError());
+  }
+  CUtensorMap tm_hi, tm_lo;
+  for (int which = 0; which < 2; ++which) {
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(A), static_cast<uint64_t>(guide_batch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(A) * D * 4};
+    uint32_t box[3] = {KC, 128, 1};
+    rc = encode_tmap(which == 0 ? &tm_hi : &tm_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, which == 0 ? g_hi : g_lo,
+                     dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+  }
   K1Args a;
+  a.timing = g_k1_timing;
+  a.inv_norm_a = g_inv;
+  // full 128-row tiles go to the tensor cores; a short tail (<= MAX_REM rows) to the CUDA cores
+  a.n_mma_tiles = (A % 128 != 0 && A % 128 <= MAX_REM) ? A / 128 : (A + 127) / 128;
+  a.n_stages = a.n_mma_tiles <= 2 ? 2 : 1;
   a.text = text_dev;
   a.guide = guide_dev;
   a.n_text = n_text;
@@ -698,7 +837,7 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   FD_REQUIRE(chunks <= 65535, "fd_sim_blend: too many parameter chunks");
   FD_CUDA_OK(cudaFuncSetAttribute(k1_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
   dim3 grid(n_text, chunks);
-  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(a);
+  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(tm_hi, tm_lo, a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

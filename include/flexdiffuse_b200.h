@@ -142,7 +142,12 @@ int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddi
                  float*   weights_dev,       /* [n_text, n_params, T] final alt_weights (or NULL)*/
                  int32_t* status_dev,        /* [n_text, n_params] FD_BLEND_*                    */
                  float*   sim_dev,           /* [n_text, A, T] softmax matrix P (debug, or NULL) */
+                 void*    workspace_dev,     /* >= fd_sim_blend_workspace_bytes(...) scratch     */
+                 int64_t  workspace_bytes,
                  void* stream);
+
+/* Scratch needed by fd_sim_blend for the tf32 hi / lo planes and norms of the guide. */
+int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D);
 
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
  * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'

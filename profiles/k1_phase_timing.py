@@ -1,0 +1,28 @@
+'''Development aid: phase timestamps of K1's CTA (0,0): [0] setup done, [1] GEMM done,
+[2] softmax + P^T done, [3] mapping done, [4] weights done, [5] blend done (ns from [0]).'''
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from flexdiffuse_b200 import _native
+dev = torch.device('cuda:0')
+lib = _native.lib()
+lib.fd_debug_set_k1_timing.argtypes = [ctypes.c_void_p]
+buf = torch.zeros(8, dtype=torch.int64, device=dev)
+for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
+    txt = torch.randn(nb, 77, 768, device=dev)
+    img = torch.randn(1, 257, 768, device=dev)
+    prm = _native.TweenParams()
+    prm.threshold_floor = prm.threshold_mult = prm.max_guidance = 0.5
+    prm.header_max, prm.align_mode, prm.mapping_reuse = 0.15, mode, reuse
+    lin = torch.linspace(0.0, 0.5, 77)[None].to(dev)
+    for _ in range(2):
+        _native.sim_blend(txt, img, [prm], lin)
+    torch.cuda.synchronize()
+    lib.fd_debug_set_k1_timing(buf.data_ptr())
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); _native.sim_blend(txt, img, [prm], lin); b.record()
+    torch.cuda.synchronize()
+    lib.fd_debug_set_k1_timing(None)
+    t = buf.cpu().tolist()
+    print(f'prompts={nb} mode={mode} reuse={reuse}: kernel {a.elapsed_time(b)*1e3:.1f} us; '
+          f'phases ns {[t[i] - t[0] for i in range(6)]}')
