@@ -36,17 +36,15 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int NPAD = 80;          // UMMA N (text tokens padded)
 constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
 constexpr int KC = 32;            // fp32 per K chunk (one 128 B swizzle row)
-constexpr int A_TILE_BYTES = 128 * 128;
-constexpr int B_TILE_BYTES = NPAD * 128;
-constexpr int STAGE_BYTES = 2 * MAX_TILES * A_TILE_BYTES + 2 * B_TILE_BYTES;  // 118,784 (3 tiles)
-constexpr int MAX_REM = 8;        // guide rows past the last full tile that go to the CUDA cores
+constexpr int TXT_TILE_BYTES = 128 * 128;  // M operand: 128 rows (80 used) x 128 B, hi and lo
+constexpr int MAX_A = MAX_TILES * 128;     // 384 guide tokens
+constexpr int MAX_REM = 8;        // guide rows past the last multiple of 16 that go to the CUDA cores
 constexpr int TEXT_WARPS = K1_WARPS - 2;
 constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 320
-constexpr int PT_STRIDE = MAX_TILES * 128;                                   // floats per P^T row
+constexpr int PT_STRIDE = MAX_A + 1;   // floats per P^T row; odd => conflict-free row-per-lane stores
 constexpr int MAXT = 80;
 constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 2
 
-static_assert((MAXT - 1) * PT_STRIDE * 4 <= STAGE_BYTES + 8192, "P^T must fit the staging area");
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
 static long long* g_k1_timing = nullptr;
@@ -65,7 +63,7 @@ struct K1Args {
   const float* text;     // [n_text, T, D]
   const float* guide;    // [guide_batch, A, D]
   const float* inv_norm_a;  // [guide_batch, A] from the prep kernel
-  int n_mma_tiles, n_stages;
+  int a_mma, n_pad, n_stages;  // guide rows on the tensor cores, padded to 16, pipeline depth
   int n_text, guide_batch, T, A, D;
   const fd_tween_params* params;  // device [n_params]
   const float* lin_w;             // device [n_params, T]
@@ -96,8 +94,9 @@ struct K1Smem {
   uint32_t tmem_slot;
 };
 
-constexpr int K1_STAGE_AREA = 2 * (2 * 2 * A_TILE_BYTES + 2 * B_TILE_BYTES);  // 172,032: two 2-tile stages
-static_assert(K1_STAGE_AREA >= STAGE_BYTES + 8192, "stage area must also hold one 3-tile stage and P^T");
+constexpr int K1_STAGE_AREA = 2 * (2 * TXT_TILE_BYTES + 2 * 256 * 128);  // 196,608: two stages at A <= 256
+static_assert(K1_STAGE_AREA >= 2 * TXT_TILE_BYTES + 2 * MAX_A * 128, "one stage at A = 384 must fit");
+static_assert(K1_STAGE_AREA >= MAXT * PT_STRIDE * 4, "the logits / P^T matrix aliases the stage area");
 constexpr int K1_SMEM_BYTES = 1024 + K1_STAGE_AREA + sizeof(K1Smem);
 
 __device__ __forceinline__ void argmax_combine(float& s, int& i, float os, int oi) {
@@ -177,14 +176,17 @@ __global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restr
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
 k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const __grid_constant__ CUtensorMap tm_hi2, const __grid_constant__ CUtensorMap tm_lo2,
                     const K1Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  // stage s: [hi tiles][lo tiles][text hi][text lo]
-  const int n_mma = a.n_mma_tiles;
-  const uint32_t stage_bytes = 2u * n_mma * A_TILE_BYTES + 2u * B_TILE_BYTES;
-  float* pt = reinterpret_cast<float*>(stage);  // aliases the staging area after the GEMM
+  // stage s: [text hi][text lo][guide hi: n_pad rows][guide lo: n_pad rows]
+  const int n_pad = a.n_pad;
+  const uint32_t g_plane = static_cast<uint32_t>(n_pad) * 128u;
+  const uint32_t stage_bytes = 2u * TXT_TILE_BYTES + 2u * g_plane;
+  float* pt_full = reinterpret_cast<float*>(stage);  // [T][PT_STRIDE] logits, then probabilities
+  float* pt = pt_full + PT_STRIDE;  // row r <-> text token r + 1 (header row dropped, guidance.py:55)
   K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + K1_STAGE_AREA);
 
   const int tid = threadIdx.x;
@@ -195,7 +197,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   const int b_idx = blockIdx.x;
   const float* text = a.text + static_cast<size_t>(b_idx) * T * D;
   const float* guide = a.guide + (a.guide_batch == 1 ? 0 : static_cast<size_t>(b_idx) * A * D);
-  const uint32_t tmem_cols = 256;  // 3 x 80 = 240 -> next power of two
+  const uint32_t tmem_cols = n_pad <= 256 ? 256 : 512;  // lane = text token, column = guide token
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_hi);
@@ -221,41 +223,52 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   const int num_kc = D / KC;
   const int nst = a.n_stages;
   const int g_idx = a.guide_batch == 1 ? 0 : b_idx;
+  const int n_blk0 = min(n_pad, 256), n_blk1 = n_pad - n_blk0;  // UMMA N of the one or two column blocks
   if (warp == 0) {
-    // ---- TMA producer: guide hi / lo tiles of every K chunk
+    // ---- TMA producer: guide hi / lo rows of every K chunk
     if (elect_one()) {
       for (int kc = 0; kc < num_kc; ++kc) {
         const int st = kc % nst;
         const uint32_t ph = (kc / nst) & 1;
         mbar_wait_backoff(&sm.empty_bar[st], ph ^ 1);
-        mbar_expect_tx(&sm.full_bar[st], 2u * n_mma * A_TILE_BYTES);
-        uint8_t* base = stage + st * stage_bytes;
-        for (int t = 0; t < n_mma; ++t) {
-          tma_load_3d(base + t * A_TILE_BYTES, &tm_hi, &sm.full_bar[st], kc * KC, t * 128, g_idx);
-          tma_load_3d(base + (n_mma + t) * A_TILE_BYTES, &tm_lo, &sm.full_bar[st], kc * KC, t * 128, g_idx);
+        mbar_expect_tx(&sm.full_bar[st], 2u * g_plane);
+        uint8_t* gb_hi = stage + st * stage_bytes + 2 * TXT_TILE_BYTES;
+        uint8_t* gb_lo = gb_hi + g_plane;
+        tma_load_3d(gb_hi, &tm_hi, &sm.full_bar[st], kc * KC, 0, g_idx);
+        tma_load_3d(gb_lo, &tm_lo, &sm.full_bar[st], kc * KC, 0, g_idx);
+        if (n_blk1 > 0) {
+          tma_load_3d(gb_hi + 256 * 128, &tm_hi2, &sm.full_bar[st], kc * KC, 256, g_idx);
+          tma_load_3d(gb_lo + 256 * 128, &tm_lo2, &sm.full_bar[st], kc * KC, 256, g_idx);
         }
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer
+    // ---- MMA issuer: D[text j, guide i] += text(128 x 8) . guide(N x 8)^T, three tf32 products
     if (elect_one()) {
-      const uint32_t idesc = umma_idesc(UMMA_TF32, 128, NPAD, 0, 0);
+      const uint32_t idesc0 = umma_idesc(UMMA_TF32, 128, n_blk0, 0, 0);
+      const uint32_t idesc1 = umma_idesc(UMMA_TF32, 128, n_blk1 > 0 ? n_blk1 : 16, 0, 0);
       for (int kc = 0; kc < num_kc; ++kc) {
         const int st = kc % nst;
         mbar_wait_backoff(&sm.full_bar[st], (kc / nst) & 1);
         tc_fence_after();
         uint8_t* base = stage + st * stage_bytes;
-        const uint64_t bh = umma_desc_sw128(smem_u32(base + 2 * n_mma * A_TILE_BYTES), 16, 1024);
-        const uint64_t bl = umma_desc_sw128(smem_u32(base + 2 * n_mma * A_TILE_BYTES + B_TILE_BYTES), 16, 1024);
-        for (int t = 0; t < n_mma; ++t) {
-          const uint64_t ah = umma_desc_sw128(smem_u32(base + t * A_TILE_BYTES), 16, 1024);
-          const uint64_t al = umma_desc_sw128(smem_u32(base + (n_mma + t) * A_TILE_BYTES), 16, 1024);
-          const uint32_t d = tmem_base + t * NPAD;
+        const uint64_t th = umma_desc_sw128(smem_u32(base), 16, 1024);
+        const uint64_t tl = umma_desc_sw128(smem_u32(base + TXT_TILE_BYTES), 16, 1024);
+        const uint64_t gh = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES), 16, 1024);
+        const uint64_t gl = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES + g_plane), 16, 1024);
 #pragma unroll
-          for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
-            mma_tf32_ss(d, al + 2 * ks, bh + 2 * ks, idesc, (kc | ks) != 0);  // small terms first
-            mma_tf32_ss(d, ah + 2 * ks, bl + 2 * ks, idesc, 1);
-            mma_tf32_ss(d, ah + 2 * ks, bh + 2 * ks, idesc, 1);
+        for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
+          mma_tf32_ss(tmem_base, tl + 2 * ks, gh + 2 * ks, idesc0, (kc | ks) != 0);  // small terms first
+          mma_tf32_ss(tmem_base, th + 2 * ks, gl + 2 * ks, idesc0, 1);
+          mma_tf32_ss(tmem_base, th + 2 * ks, gh + 2 * ks, idesc0, 1);
+        }
+        if (n_blk1 > 0) {
+          const uint64_t gh2 = gh + ((256 * 128) >> 4), gl2 = gl + ((256 * 128) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            mma_tf32_ss(tmem_base + 256, tl + 2 * ks, gh2 + 2 * ks, idesc1, (kc | ks) != 0);
+            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gl2 + 2 * ks, idesc1, 1);
+            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gh2 + 2 * ks, idesc1, 1);
           }
         }
         tc_commit(&sm.empty_bar[st]);
@@ -283,12 +296,12 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     for (int kc = 0; kc < num_kc; ++kc) {
       const int st = kc % nst;
       mbar_wait(&sm.empty_bar[st], ((kc / nst) & 1) ^ 1);
-      uint8_t* b_hi = stage + st * stage_bytes + 2 * n_mma * A_TILE_BYTES;
-      uint8_t* b_lo = b_hi + B_TILE_BYTES;
+      uint8_t* t_hi = stage + st * stage_bytes;
+      uint8_t* t_lo = t_hi + TXT_TILE_BYTES;
 #pragma unroll
       for (int j = 0; j < B_ITEMS; ++j) {
         const int f = tt + j * TEXT_THREADS;
-        if (f < NPAD * 8) {  // rows T..79 are written as zeros
+        if (f < NPAD * 8) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
           const float4 v = rb[j];
           const uint32_t off = sw128_offset(f >> 3, f & 7);
           float4 h, l;
@@ -300,8 +313,8 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           l.y = v.y - h.y;
           l.z = v.z - h.z;
           l.w = v.w - h.w;
-          *reinterpret_cast<float4*>(b_hi + off) = h;
-          *reinterpret_cast<float4*>(b_lo + off) = l;
+          *reinterpret_cast<float4*>(t_hi + off) = h;
+          *reinterpret_cast<float4*>(t_lo + off) = l;
           ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         }
       }
@@ -320,12 +333,11 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       const int f = tt + j * TEXT_THREADS;
       if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
     }
-    // remainder guide rows (A - 128 * n_mma <= 8) on the CUDA cores, exact fp32: warp w takes
+    // remainder guide rows (A - a_mma <= 8) on the CUDA cores, exact fp32: warp w takes
     // text tokens w, w + 10, ...
-    const int rem0 = n_mma * 128;
-    const int n_rem = A - rem0;
+    const int n_rem = A - a.a_mma;
     if (n_rem > 0) {
-      const float* gr = a.guide + (static_cast<size_t>(g_idx) * A + rem0) * D;
+      const float* gr = a.guide + (static_cast<size_t>(g_idx) * A + a.a_mma) * D;
       for (int j = warp - 2; j < T; j += TEXT_WARPS) {
         float acc[MAX_REM];
 #pragma unroll
@@ -342,10 +354,12 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
 #pragma unroll
         for (int r = 0; r < MAX_REM; ++r) {
-          float v = acc[r];
+          if (r < n_rem) {  // warp-uniform
+            float v = acc[r];
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (lane == 0 && r < n_rem) sm.rem[r][j] = v;
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) sm.rem[r][j] = v;
+          }
         }
       }
     }
@@ -353,60 +367,72 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   for (int i = tid; i < A; i += K1_THREADS) sm.inv_norm_a[i] = a.inv_norm_a[static_cast<size_t>(g_idx) * A + i];
   mbar_wait(&sm.done_bar, 0);
   tc_fence_after();
-  __syncthreads();  // norms + remainder rows visible; staging area free for P^T
+  __syncthreads();  // norms + remainder rows visible; staging area free for the logits matrix
   K1_STAMP(1);
 
-  // ------------------------------------------------------------------ 2. softmax per lane
+  // ------------------------------------------------------------------ 2. logits -> smem, softmax per guide token
   {
-    const int tile = warp >> 2, quarter = warp & 3;
-    if (tile < n_tiles) {
-      const int i = tile * 128 + quarter * 32 + lane;
-      float l[NPAD];
-      if (tile < n_mma) {
-        uint32_t v[NPAD / 16][16];
+    // 2a. TMEM lane j (text token) -> row j of the logits matrix; 100 * cos in the log2 domain
+    if (warp < 4) {
+      const int j = warp * 32 + lane;
+      const float sb = (j < T) ? sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) : 0.f;
+      for (int c0 = 0; c0 < a.a_mma; c0 += 64) {
+        uint32_t v[4][16];
 #pragma unroll
-        for (int c = 0; c < NPAD / 16; ++c)
-          tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * NPAD + 16 * c, v[c]);
+        for (int g = 0; g < 4; ++g)
+          if (c0 + 16 * g < n_pad) tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0 + 16 * g, v[g]);
         tmem_ld_wait();
+        if (j < T) {
 #pragma unroll
-        for (int c = 0; c < NPAD / 16; ++c)
+          for (int g = 0; g < 4; ++g)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) l[16 * c + q] = __uint_as_float(v[c][q]);
-      } else {
-        const int r = min(max(i - n_mma * 128, 0), MAX_REM - 1);
-#pragma unroll
-        for (int j = 0; j < NPAD; ++j) l[j] = sm.rem[r][j];
+            for (int q = 0; q < 16; ++q) {
+              const int i = c0 + 16 * g + q;
+              if (i < a.a_mma) pt_full[j * PT_STRIDE + i] = __uint_as_float(v[g][q]) * sb * sm.inv_norm_a[i];
+            }
+        }
       }
-      if (i < A) {
-        // logits 100 * cos(guide_i, text_j) (guidance.py:43-50) in the log2 domain
-        const float ia = sm.inv_norm_a[i] * (100.0f * 1.4426950408889634f);
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NPAD; ++j) {
-          l[j] = (j < T) ? l[j] * ia * sm.inv_norm_b[j] : -INFINITY;
-          mx = fmaxf(mx, l[j]);
-        }
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < NPAD; j += 2) {
-          l[j] = ex2_approx(l[j] - mx);  // padded columns: 2^-inf = 0
-          l[j + 1] = ex2_approx(l[j + 1] - mx);
-          s0 += l[j];
-          s1 += l[j + 1];
-        }
-        const float inv = 1.0f / (s0 + s1);
-        float* simrow = (a.sim && blockIdx.y == 0) ? a.sim + (static_cast<size_t>(b_idx) * A + i) * T : nullptr;
-#pragma unroll
-        for (int j = 0; j < NPAD; ++j) {
-          if (j < T) {
-            const float p = l[j] * inv;
-            if (j >= 1) pt[(j - 1) * PT_STRIDE + i] = p;  // header column dropped (guidance.py:55)
-            if (simrow) simrow[j] = p;
-          }
-        }
+      tc_fence_before();
+    } else {
+      // remainder guide rows computed on the CUDA cores
+      const int n_rem = A - a.a_mma;
+      for (int idx = tid - 128; idx < n_rem * T; idx += K1_THREADS - 128) {
+        const int r = idx / T, j = idx - r * T;
+        pt_full[j * PT_STRIDE + a.a_mma + r] =
+            sm.rem[r][j] * sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) * sm.inv_norm_a[a.a_mma + r];
       }
     }
-    tc_fence_before();
+    __syncthreads();
+    K1_STAMP(6);
+    // 2b. softmax over the T text tokens of each guide token (one thread per column; lanes walk
+    //     consecutive addresses => conflict free)
+    for (int i = tid; i < A; i += K1_THREADS) {
+      float mx = -INFINITY;
+      for (int j = 0; j < T; ++j) mx = fmaxf(mx, pt_full[j * PT_STRIDE + i]);
+      float s0 = 0.f, s1 = 0.f;
+      int j = 0;
+      for (; j + 1 < T; j += 2) {
+        const float e0 = ex2_approx(pt_full[j * PT_STRIDE + i] - mx);
+        const float e1 = ex2_approx(pt_full[(j + 1) * PT_STRIDE + i] - mx);
+        pt_full[j * PT_STRIDE + i] = e0;
+        pt_full[(j + 1) * PT_STRIDE + i] = e1;
+        s0 += e0;
+        s1 += e1;
+      }
+      if (j < T) {
+        const float e0 = ex2_approx(pt_full[j * PT_STRIDE + i] - mx);
+        pt_full[j * PT_STRIDE + i] = e0;
+        s0 += e0;
+      }
+      const float inv = 1.0f / (s0 + s1);
+      float* simrow = (a.sim && blockIdx.y == 0) ? a.sim + (static_cast<size_t>(b_idx) * A + i) * T : nullptr;
+      for (j = 0; j < T; ++j) {
+        const float p = pt_full[j * PT_STRIDE + i] * inv;
+        pt_full[j * PT_STRIDE + i] = p;
+        if (simrow) simrow[j] = p;
+      }
+    }
+    K1_STAMP(7);
   }
   __syncthreads();
 
@@ -794,21 +820,28 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
     k1_prep_guide_kernel<<<(rows + 7) / 8, 256, 0, cst>>>(guide_dev, g_hi, g_lo, g_inv, rows, D);
     FD_CUDA_OK(cudaGetLastError());
   }
-  CUtensorMap tm_hi, tm_lo;
-  for (int which = 0; which < 2; ++which) {
-    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(A), static_cast<uint64_t>(guide_batch)};
+  // rows handled by the tensor cores: everything except a short (<= MAX_REM) tail past a multiple of 16
+  const int rem = A % 16;
+  const int a_mma = (rem != 0 && rem <= MAX_REM && A > 16) ? A - rem : A;
+  const int n_pad = (a_mma + 15) / 16 * 16;
+  const int n_blk0 = n_pad < 256 ? n_pad : 256, n_blk1 = n_pad - n_blk0;
+  CUtensorMap tm_hi, tm_lo, tm_hi2, tm_lo2;
+  for (int which = 0; which < 4; ++which) {
+    // rows >= a_mma of a box are never used: keep them out of the map so TMA zero-fills them
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), static_cast<uint64_t>(guide_batch)};
     uint64_t strides[2] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(A) * D * 4};
-    uint32_t box[3] = {KC, 128, 1};
-    rc = encode_tmap(which == 0 ? &tm_hi : &tm_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, which == 0 ? g_hi : g_lo,
-                     dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    uint32_t box[3] = {KC, static_cast<uint32_t>(which < 2 ? n_blk0 : (n_blk1 > 0 ? n_blk1 : 16)), 1};
+    CUtensorMap* dst = which == 0 ? &tm_hi : which == 1 ? &tm_lo : which == 2 ? &tm_hi2 : &tm_lo2;
+    rc = encode_tmap(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (which & 1) ? g_lo : g_hi, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
   K1Args a;
   a.timing = g_k1_timing;
   a.inv_norm_a = g_inv;
-  // full 128-row tiles go to the tensor cores; a short tail (<= MAX_REM rows) to the CUDA cores
-  a.n_mma_tiles = (A % 128 != 0 && A % 128 <= MAX_REM) ? A / 128 : (A + 127) / 128;
-  a.n_stages = a.n_mma_tiles <= 2 ? 2 : 1;
+  a.a_mma = a_mma;
+  a.n_pad = n_pad;
+  a.n_stages = (2 * (2 * TXT_TILE_BYTES + 2 * n_pad * 128) <= K1_STAGE_AREA) ? 2 : 1;
   a.text = text_dev;
   a.guide = guide_dev;
   a.n_text = n_text;
@@ -837,7 +870,7 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   FD_REQUIRE(chunks <= 65535, "fd_sim_blend: too many parameter chunks");
   FD_CUDA_OK(cudaFuncSetAttribute(k1_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
   dim3 grid(n_text, chunks);
-  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(tm_hi, tm_lo, a);
+  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(tm_hi, tm_lo, tm_hi2, tm_lo2, a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

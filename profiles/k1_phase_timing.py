@@ -25,4 +25,4 @@ for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
     lib.fd_debug_set_k1_timing(None)
     t = buf.cpu().tolist()
     print(f'prompts={nb} mode={mode} reuse={reuse}: kernel {a.elapsed_time(b)*1e3:.1f} us; '
-          f'phases ns {[t[i] - t[0] for i in range(6)]}')
+          f'phases ns {[t[i] - t[0] for i in range(6)]} softmax-internal {[t[6]-t[0], t[7]-t[0]]}')
