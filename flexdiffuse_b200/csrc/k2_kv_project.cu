@@ -6,43 +6,46 @@
 //   out[M, N] = ctx[M, K] . w[N, K]^T      bf16 operands, fp32 accumulate, bf16 out
 //   M = n_ctx * 80 (context rows, zero padded 77 -> 80), K = 768, N = 24960 (all to_k|to_v rows)
 //
-// Warp-specialised tcgen05 GEMM: warp 0 = TMA producer (SWIZZLE_128B K-major tiles),
-// warp 1 = single-thread tcgen05.mma issuer (accumulator 128x128 fp32 in TMEM),
-// warps 2-5 = epilogue (tcgen05.ld -> bf16 -> global).  4-stage mbarrier ring.
-// Grid: m-tile fastest so the CTAs sharing one weight tile run together (weight tile read from
-// HBM once, the other m-tiles hit L2).
+// v2: persistent, warp-specialised tcgen05 GEMM, one CTA per SM walking over 128 x 256 tiles
+// (m fastest, so the CTAs running together share one weight tile in L2):
+//   warp 0     : TMA producer, 4-stage mbarrier ring of {A 128x64, B 256x64} SWIZZLE_128B tiles
+//   warp 1     : single-thread tcgen05.mma issuer (M128 N256 K16), accumulator in TMEM
+//   warps 2-5  : epilogue (tcgen05.ld -> bf16 -> global)
+// The accumulator is double-buffered (2 x 256 TMEM columns), so the epilogue of tile i runs under
+// the mainloop of tile i+1.  v1 (one 128x128 tile per CTA, no overlap) was bound by L2->SM operand
+// traffic at 64 FLOP/B per tile (profiles/r01/SUMMARY.md); 128x256 tiles need 25 % fewer bytes.
 #include "fd_common.cuh"
 
 namespace fd {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 128;
+constexpr int BN = 256;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int K2_THREADS = 192;
-constexpr int K2_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*bars*/;
+constexpr int K2_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*bars*/;
+constexpr int TMEM_COLS = 2 * BN;
 
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               __nv_bfloat16* __restrict__ out, int M, int N, int K) {
+               __nv_bfloat16* __restrict__ out, int M, int N, int K, int m_tiles, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_blk = blockIdx.x;
-  const int n_blk = blockIdx.y;
   const int num_kb = K / BK;
+  const int total_tiles = m_tiles * n_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
@@ -51,11 +54,14 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -65,65 +71,87 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   if (warp == 0) {
     if (elect_one()) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_2d(smem_a + s * A_STAGE_BYTES, &tm_a, &full_bar[s], kb * BK, m_blk * BM);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &tm_b, &full_bar[s], kb * BK, n_blk * BN);
+      int it = 0;  // running k-block counter across tiles: stage = it % STAGES
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_backoff(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+          tma_load_2d(smem + s * STAGE_BYTES, &tm_a, &full_bar[s], kb * BK, m_blk * BM);
+          tma_load_2d(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tm_b, &full_bar[s], kb * BK, n_blk * BN);
+        }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(UMMA_BF16, BM, BN, 0, 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, local = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        const int acc = local & 1;
+        mbar_wait_backoff(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
-        const uint64_t adesc = umma_desc_sw128(smem_u32(smem_a + s * A_STAGE_BYTES), 16, 1024);
-        const uint64_t bdesc = umma_desc_sw128(smem_u32(smem_b + s * B_STAGE_BYTES), 16, 1024);
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait_backoff(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES), 16, 1024);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // advance 16 bf16 = 32 B along K inside the swizzle row: +2 in the (addr >> 4) field
-          mma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < BK / 16; ++k)  // 16 bf16 = 32 B along K inside the swizzle row: +2
+            mma_f16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
         }
-        tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+        tc_commit(&tmem_full[acc]);  // accumulator complete
       }
-      tc_commit(tmem_full_bar);  // accumulator complete
     }
   } else {
     // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
     const int quarter = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int row = quarter * 32 + lane;
-    const int64_t g_row = static_cast<int64_t>(m_blk) * BM + row;
-    const int n0 = n_blk * BN;
+    int local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
+      const int acc = local & 1;
+      mbar_wait(&tmem_full[acc], (local >> 1) & 1);
+      tc_fence_after();
+      const int64_t g_row = static_cast<int64_t>(m_blk) * BM + row;
+      const int n0 = n_blk * BN;
+      const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t v[16];
-      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c, v);
-      tmem_ld_wait();
-      if (g_row < M) {
-        uint32_t pk[8];
+      for (int c0 = 0; c0 < BN; c0 += 64) {
+        uint32_t v[4][16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-          pk[j] = *reinterpret_cast<uint32_t*>(&b);
+        for (int g = 0; g < 4; ++g) tmem_ld_x16(tbase + c0 + 16 * g, v[g]);
+        tmem_ld_wait();
+        if (g_row < M) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int c = c0 + 16 * g;
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              __nv_bfloat162 b =
+                  __floats2bfloat162_rn(__uint_as_float(v[g][2 * j]), __uint_as_float(v[g][2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&b);
+            }
+            __nv_bfloat16* dst = out + g_row * N + n0 + c;
+            if (n0 + c + 8 <= N) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (n0 + c + 16 <= N) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
         }
-        __nv_bfloat16* dst = out + g_row * N + n0 + c;
-        if (n0 + c + 8 <= N) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        if (n0 + c + 16 <= N) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -161,14 +189,19 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
+  static thread_local int attr_device = -1;
+  int dev = 0;
+  FD_CUDA_OK(cudaGetDevice(&dev));
+  if (attr_device != dev) {
     FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
-    attr_set = true;
+    attr_device = dev;
   }
-  dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
-  k2_gemm_kernel<<<grid, K2_THREADS, K2_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      tm_a, tm_b, static_cast<__nv_bfloat16*>(out_bf16_dev), M, N, K);
+  const int sms = sm_count();
+  if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_kv_project: cannot query SM count");
+  const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles;
+  k2_gemm_kernel<<<total < sms ? total : sms, K2_THREADS, K2_SMEM, static_cast<cudaStream_t>(stream)>>>(
+      tm_a, tm_b, static_cast<__nv_bfloat16*>(out_bf16_dev), M, N, K, m_tiles, n_tiles);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }
