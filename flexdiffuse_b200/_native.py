@@ -27,7 +27,8 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sim_blend_workspace_bytes',
                'fd_kv_project', 'fd_cross_attn',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
-               'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu')
+               'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
+               'fd_composite_eps')
 
 
 class NativeError(RuntimeError):
@@ -39,6 +40,12 @@ class SchedCoeffs(C.Structure):
     _fields_ = [('guidance', C.c_float), ('use_cfg', C.c_int),
                 ('w', C.c_float * 4), ('a', C.c_float), ('b', C.c_float),
                 ('c_noise', C.c_float), ('in_scale', C.c_float)]
+
+
+class EntityBox(C.Structure):
+    '''struct fd_entity_box'''
+    _fields_ = [('ox', C.c_int), ('oy', C.c_int), ('sx', C.c_int), ('sy', C.c_int),
+                ('blend', C.c_float)]
 
 
 class TweenParams(C.Structure):
@@ -108,6 +115,9 @@ def lib() -> C.CDLL:
     l.fd_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int,
                                    C.c_float, vp]
     l.fd_add_layernorm.restype = C.c_int
+    l.fd_composite_eps.argtypes = [vp, C.c_int, C.POINTER(EntityBox), C.c_int, C.c_int,
+                                   C.c_int, C.c_int, vp, vp, vp]
+    l.fd_composite_eps.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
     l.fd_geglu.restype = C.c_int
     if l.fd_version() != FD_ABI_VERSION:
@@ -385,3 +395,20 @@ def add_layernorm(x: torch.Tensor, y: Optional[torch.Tensor], gamma: torch.Tenso
     check(rc, 'fd_add_layernorm')
     count_launch()
     return (total if y is not None else x), norm
+
+
+def composite_eps(eps_all: torch.Tensor, boxes: Sequence[EntityBox]):
+    '''fd_composite_eps: eps_all [2+E, C, H, W] (uncond, background, entities; NCHW contiguous)
+    -> (uncond fp32 [1,C,H,W], composite conditional fp32 [1,C,H,W]).'''
+    _need(eps_all, 'eps_all')
+    n, Cc, H, W = eps_all.shape
+    if n != 2 + len(boxes):
+        raise NativeError(f'eps_all has {n} samples, expected {2 + len(boxes)}')
+    u = torch.empty((1, Cc, H, W), dtype=torch.float32, device=eps_all.device)
+    c = torch.empty_like(u)
+    arr = (EntityBox * max(len(boxes), 1))(*boxes)
+    rc = lib().fd_composite_eps(ptr(eps_all), dtype_code(eps_all.dtype), arr, len(boxes),
+                                Cc, H, W, ptr(u), ptr(c), stream_ptr(eps_all.device))
+    check(rc, 'fd_composite_eps')
+    count_launch()
+    return u, c

@@ -136,6 +136,71 @@ void launch_nh(int nh, dim3 grid, cudaStream_t st, const K4Args& a) {
 }  // namespace
 }  // namespace fd
 
+namespace fd {
+namespace {
+
+constexpr int MAX_ENTITIES = 16;
+struct K9Args {
+  const void* eps;  // [2 + E, C, H, W]: uncond, background, entities
+  float* out_u;     // [C, H, W] fp32 copy of the uncond prediction
+  float* out_c;     // [C, H, W] fp32 composite conditional prediction
+  int C, H, W, E;
+  fd_entity_box box[MAX_ENTITIES];
+};
+
+// K9: rectangular per-entity lerp of the entity noise predictions into the background prediction
+// (composition/guide.py:66-87), entities applied in declaration order.
+template <bool BF16>
+__global__ void __launch_bounds__(256) k9_composite_eps_kernel(const K9Args a) {
+  const int plane = a.H * a.W, chw = a.C * plane;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += gridDim.x * blockDim.x) {
+    const int pix = i % plane, y = pix / a.W, x = pix - y * a.W;
+    auto ld = [&](int sample) -> float {
+      if constexpr (BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a.eps)[sample * chw + i]);
+      else return reinterpret_cast<const float*>(a.eps)[sample * chw + i];
+    };
+    float v = ld(1);
+    for (int e = 0; e < a.E; ++e) {
+      const fd_entity_box b = a.box[e];
+      if (x >= b.ox && x < b.ox + b.sx && y >= b.oy && y < b.oy + b.sy) v = v + b.blend * (ld(2 + e) - v);
+    }
+    a.out_u[i] = ld(0);
+    a.out_c[i] = v;
+  }
+}
+
+}  // namespace
+}  // namespace fd
+
+extern "C" int fd_composite_eps(const void* eps_dev, int eps_dtype, const fd_entity_box* boxes, int n_entities,
+                                int C, int H, int W, float* out_uncond_dev, float* out_cond_dev, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(eps_dev && out_uncond_dev && out_cond_dev, "fd_composite_eps: NULL pointer");
+  FD_REQUIRE(n_entities >= 0 && n_entities <= MAX_ENTITIES, "fd_composite_eps: at most %d entities", MAX_ENTITIES);
+  FD_REQUIRE(n_entities == 0 || boxes, "fd_composite_eps: boxes is NULL");
+  FD_REQUIRE(C > 0 && H > 0 && W > 0, "fd_composite_eps: non-positive shape");
+  FD_REQUIRE(eps_dtype == FD_DTYPE_F32 || eps_dtype == FD_DTYPE_BF16, "fd_composite_eps: bad dtype");
+  int rc = check_device();
+  if (rc != FD_OK) return rc;
+  K9Args a;
+  a.eps = eps_dev;
+  a.out_u = out_uncond_dev;
+  a.out_c = out_cond_dev;
+  a.C = C;
+  a.H = H;
+  a.W = W;
+  a.E = n_entities;
+  for (int e = 0; e < n_entities; ++e) a.box[e] = boxes[e];
+  const int chw = C * H * W;
+  const int grid = (chw + 255) / 256;
+  if (eps_dtype == FD_DTYPE_BF16)
+    k9_composite_eps_kernel<true><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  else
+    k9_composite_eps_kernel<false><<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
+}
+
 extern "C" int fd_cfg_sched_step(const void* eps_uncond_dev, const void* eps_cond_dev,
                                  int eps_dtype, const float* x_dev, const float* h1_dev,
                                  const float* h2_dev, const float* h3_dev,

@@ -87,7 +87,7 @@ class SimpleGuide(GuideBase):
     def _runner(self, latents: torch.Tensor):
         self._ensure_cache()
         return self.unet.graph_runner(latents.shape, self._kv.n_ctx,
-                                      self.classifier_free_guidance)
+                                      2 if self.classifier_free_guidance else 1)
 
     def model_input_buffer(self, latents: torch.Tensor) -> torch.Tensor:
         '''bf16 [B,4,h,w] buffer the UNet reads; K4 can write the next step's model input

@@ -415,13 +415,14 @@ class UNet2DConditionModel(nn.Module):
     def set_attention_slice(self, slice_size):  # flex.py:102; memory knob only
         self._attention_slice = slice_size
 
-    def graph_runner(self, latent_shape, n_ctx: int, cfg: bool) -> 'UNetGraphRunner':
-        '''CUDA-graph runner for one (latent shape, #contexts, CFG) signature, shared by every
+    def graph_runner(self, latent_shape, n_ctx: int, repeat: int) -> 'UNetGraphRunner':
+        '''CUDA-graph runner for one (latent shape, #contexts, #copies of the latents) signature
+        (CFG evaluates the latents twice, a composite guide 2 + #entities times), shared by every
         guide with that signature (capturing costs ~100 ms, replaying ~nothing).'''
-        key = (tuple(latent_shape), n_ctx, cfg)
+        key = (tuple(latent_shape), n_ctx, int(repeat))
         runners = self.__dict__.setdefault('_graph_runners', {})
         if key not in runners:
-            runners[key] = UNetGraphRunner(self, latent_shape, n_ctx, cfg)
+            runners[key] = UNetGraphRunner(self, latent_shape, n_ctx, int(repeat))
         return runners[key]
 
     # ------------------------------------------------------------------ forward
@@ -472,10 +473,10 @@ class UNetGraphRunner:
     Static buffers: bf16 model input [B,4,h,w] (K4 writes the next step's input straight into
     it), the sinusoidal timestep row, the K2 cache and the sample->context index.  A guide
     "owns" the runner while its cache is loaded; switching guides costs one D2D copy.'''
-    def __init__(self, unet: UNet2DConditionModel, latent_shape, n_ctx: int, cfg: bool):
+    def __init__(self, unet: UNet2DConditionModel, latent_shape, n_ctx: int, repeat: int):
         dev = unet.conv_in.weight.device
         dt = unet.conv_in.weight.dtype
-        self.unet, self.cfg = unet, cfg
+        self.unet, self.repeat = unet, repeat
         self.static_in = torch.zeros(tuple(latent_shape), dtype=dt, device=dev)
         self.static_temb = torch.zeros((1, unet.conv_in.out_channels),
                                        dtype=torch.float32, device=dev)
@@ -483,14 +484,14 @@ class UNetGraphRunner:
         self.kv = KVCache(torch.zeros((n_ctx * T_PAD, n_kv), dtype=torch.bfloat16,
                                       device=dev), n_ctx)
         B = latent_shape[0]
-        self.ctx_index = torch.zeros((2 * B if cfg else B,), dtype=torch.int32, device=dev)
+        self.ctx_index = torch.zeros((B * repeat,), dtype=torch.int32, device=dev)
         self.owner = None
         self.graph = None
         self.static_out = None
         self.native_launches = 0
 
     def _forward(self):
-        x = torch.cat([self.static_in, self.static_in]) if self.cfg else self.static_in
+        x = torch.cat([self.static_in] * self.repeat) if self.repeat > 1 else self.static_in
         return self.unet(x, None, kv_cache=self.kv, ctx_index=self.ctx_index,
                          temb_sin=self.static_temb).sample
 

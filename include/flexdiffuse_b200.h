@@ -104,6 +104,26 @@ int fd_cfg_sched_step(const void*  eps_uncond_dev,  /* [n] eps_dtype, may be NUL
                       int          scaled_dtype,
                       void*        stream);
 
+/* ---- K9: regional noise composition --------------------------------------------------- *
+ * Replaces composition/guide.py:66-87 (`CompositeGuide._guide_latents`): each entity's noise
+ * prediction is lerped into the background prediction inside its rectangle (latent blocks),
+ * entities in declaration order.  `eps` holds the UNet outputs for (uncond, background,
+ * entity 0..E-1) on the SAME latents, NCHW.  Outputs the fp32 uncond copy and the composite
+ * conditional prediction, ready for fd_cfg_sched_step.                                     */
+typedef struct fd_entity_box {
+  int   ox, oy;   /* EntityEmbeds.offset_blocks (x, y)   composition/embeds.py:13 */
+  int   sx, sy;   /* EntityEmbeds.size_blocks   (w, h)   composition/embeds.py:14 */
+  float blend;    /* EntityEmbeds.blend                   composition/embeds.py:15 */
+} fd_entity_box;
+
+int fd_composite_eps(const void* eps_dev,            /* [2 + n_entities, C, H, W] eps_dtype     */
+                     int eps_dtype,
+                     const fd_entity_box* boxes,     /* HOST [n_entities], <= 16                */
+                     int n_entities, int C, int H, int W,
+                     float* out_uncond_dev,          /* [C, H, W]                               */
+                     float* out_cond_dev,            /* [C, H, W]                               */
+                     void* stream);
+
 /* ---- K1: text-token x guide-token similarity map + re-weighting + blend ------------- *
  * Replaces  guidance.py:23-85    _map_emb            (normalise, 100*cos, softmax over the
  *                                                     text tokens, header column dropped,

@@ -26,7 +26,7 @@ from diffusers.schedulers import (DDIMScheduler, LMSDiscreteScheduler,  # noqa: 
                                   PNDMScheduler)
 
 __all__ = ['DDIMScheduler', 'LMSDiscreteScheduler', 'PNDMScheduler',
-           'noise_pred', 'denoise']
+           'noise_pred', 'denoise', 'composite_noise_pred']
 
 
 def noise_pred(unet_fn: Callable, uncond: torch.Tensor, embeds: torch.Tensor,
@@ -94,3 +94,27 @@ def denoise(unet_fn: Callable, scheduler, uncond: torch.Tensor,
         if trace is not None:
             trace.append((eps, lat))
     return lat
+
+
+def composite_noise_pred(unet_fn: Callable, uncond: torch.Tensor, background: torch.Tensor,
+                         entities, guidance: float, latents: torch.Tensor, step):
+    '''/root/reference/composition/guide.py:58-95 `CompositeGuide._guide_latents` (batch 1):
+    one UNet call on (uncond, background, entity embeds) over the same latents, rectangular
+    lerp of each entity's prediction into the background's, then CFG.
+
+    entities: list of (embed [1,77,768], (ox, oy) blocks, (sx, sy) blocks, blend).'''
+    cfg = guidance > 1.0
+    conds = [background] + [e[0] for e in entities]
+    ctx = torch.cat(([uncond] if cfg else []) + conds)
+    eps = unet_fn(torch.cat([latents] * ctx.shape[0]), step, ctx)
+    stack = eps[1:] if cfg else eps
+    out = stack[:1].clone()
+    ent = stack[1:]
+    for ei, (_, (ow, oh), (sw, sh), blend) in enumerate(entities):
+        bw, bh = ow + sw, oh + sh
+        bgs = out[:, :, oh:bh, ow:bw]
+        out[:, :, oh:bh, ow:bw] = bgs + blend * (ent[ei:ei + 1, :, oh:bh, ow:bw] - bgs)
+    if cfg:
+        u = eps[:1]
+        out = u + guidance * (out - u)
+    return out

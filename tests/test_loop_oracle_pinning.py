@@ -119,3 +119,41 @@ def test_restated_loop_equals_reference_loop(ref_mods, sched_name, img2img):
                          init_size=(64, 64), strength=0.6, eta=0.3,
                          generator=gen2)
     assert torch.equal(lat, got['lat'])
+
+
+def test_composite_restatement_equals_reference(ref_mods):
+    '''oracle composite_noise_pred == the UNMODIFIED reference CompositeGuide.noise_pred.'''
+    rflex, rguide, lo = ref_mods
+    sys.path.insert(0, REF)
+    try:
+        import composition.guide as rcomp
+        from composition.schema import EntitySchema, Schema
+    finally:
+        sys.path.remove(REF)
+
+    class Enc:
+        def __init__(self):
+            self.g = torch.Generator().manual_seed(9)
+            self.cache = {}
+
+        def prompt(self, p):
+            if p not in self.cache:
+                self.cache[p] = torch.randn(1, 77, 768, generator=self.g)
+            return self.cache[p]
+
+    enc, unet = Enc(), ToyUNet()
+    schema = Schema('a meadow', 'oil', 'ink', (0.0, 1.0), [
+        EntitySchema('a bear', (16, 8), (24, 32), 0.8),
+        EntitySchema('a hat', (24, 0), (16, 16), 0.5),
+    ])
+    x = torch.randn(1, 4, 8, 8, generator=torch.Generator().manual_seed(1))
+    for g in (7.5, 1.0):
+        guide = rcomp.CompositeGuide(enc, unet, g, schema, 20)
+        with torch.no_grad():
+            want = guide.noise_pred(x.clone(), torch.tensor(481))
+            ents = [(enc.prompt(e.prompt), tuple(v // 8 for v in e.offset),
+                     tuple(v // 8 for v in e.size), e.blend) for e in schema.entities]
+            got = lo.composite_noise_pred(lambda l, t, c: unet(l, t, c).sample, enc.prompt(''),
+                                          enc.prompt('a meadow'), ents, g, x.clone(),
+                                          torch.tensor(481))
+        assert torch.equal(got, want), g
