@@ -252,6 +252,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   return d;
 }
 
+// K-major SWIZZLE_64B: rows of 64 bytes, 8-row groups of 512 B => SBO = 512 (layout type 4).
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;
+  return d;
+}
+// byte offset of 16-byte chunk `c16` (0..3) of row `r` inside a K-major SWIZZLE_64B tile whose rows
+// are 64 bytes (Swizzle<2,4,3>: address bits [4,6) xor bits [7,9)); tile base 512-aligned.
+__device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c16) {
+  return (r >> 3) * 512u + (r & 7u) * 64u + ((c16 ^ ((r >> 1) & 3u)) << 4);
+}
+
 // Instruction descriptor (32-bit) for kind::f16 / kind::tf32, fp32 accumulate, dense:
 //   [4,6) c_format (1 = F32)  [7,10) a_format  [10,13) b_format  (0 F16, 1 BF16, 2 TF32)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4
