@@ -269,6 +269,23 @@ __device__ __forceinline__ uint32_t sw64_offset(uint32_t r, uint32_t c16) {
   return (r >> 3) * 512u + (r & 7u) * 64u + ((c16 ^ ((r >> 1) & 3u)) << 4);
 }
 
+// K-major SWIZZLE_32B: rows of 32 bytes, 8-row groups of 256 B => SBO = 256 (layout type 6).
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                   uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  d |= 6ull << 61;
+  return d;
+}
+// byte offset of 16-byte chunk `c16` (0..1) of row `r` inside a K-major SWIZZLE_32B tile whose rows
+// are 32 bytes (Swizzle<1,4,3>: address bit 4 xor bit 7); tile base 256-aligned.
+__device__ __forceinline__ uint32_t sw32_offset(uint32_t r, uint32_t c16) {
+  return (r >> 3) * 256u + (r & 7u) * 32u + ((c16 ^ ((r >> 2) & 1u)) << 4);
+}
+
 // Instruction descriptor (32-bit) for kind::f16 / kind::tf32, fp32 accumulate, dense:
 //   [4,6) c_format (1 = F32)  [7,10) a_format  [10,13) b_format  (0 F16, 1 BF16, 2 TF32)
 //   [15] a_major  [16] b_major (0 = K-major, 1 = MN-major)  [17,23) N>>3  [24,29) M>>4

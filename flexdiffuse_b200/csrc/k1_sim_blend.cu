@@ -15,7 +15,8 @@
 //      the logits are fp32-equivalent (a single bf16/tf32 pass flips arg-max / threshold
 //      decisions).  v3 used 3 tf32 products; tf32 UMMA measured ~4x slower per MAC
 //      than bf16 on this part (profiles/r01/SUMMARY.md), so 6 bf16 products are ~2.5x cheaper.
-//      Warp-specialised 2-stage pipeline over K chunks of 32 (SWIZZLE_64B): warp 0 TMA-loads the
+//      Warp-specialised pipeline over K chunks of 16 (one UMMA k-step, SWIZZLE_32B rows), up to 6
+//      stages in flight (a 2-stage version was bound by the TMA round trip): warp 0 TMA-loads the
 //      guide planes, warps 2-11 split the prompt's own chunk in registers into the same layout
 //      (+ sum of squares for its L2 norms, two chunks prefetched), warp 1 issues the MMAs.  Guide
 //      rows past the last multiple of 16 (the 257th CLIP token) are <= 8 dot products per text
@@ -37,8 +38,10 @@ constexpr int K1_THREADS = 384;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int NPAD = 80;          // UMMA N (text tokens padded)
 constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
-constexpr int KC = 32;            // elements per K chunk (one 64 B bf16 swizzle row)
-constexpr int TXT_TILE_BYTES = 128 * 64;   // M operand plane: 128 rows (80 used) x 64 B; 3 planes
+constexpr int KC = 16;            // elements per K chunk = one UMMA k-step (32 B bf16 swizzle row)
+constexpr int ROW_B = KC * 2;     // bytes per operand row in shared memory
+constexpr int MAX_STAGES = 6;
+constexpr int TXT_TILE_BYTES = 128 * ROW_B;  // M operand plane: 128 rows (80 used) x 32 B; 3 planes
 constexpr int NPLANES = 3;
 constexpr int MAX_A = MAX_TILES * 128;     // 384 guide tokens
 constexpr int MAX_REM = 8;        // guide rows past the last multiple of 16 that go to the CUDA cores
@@ -46,7 +49,8 @@ constexpr int TEXT_WARPS = K1_WARPS - 2;
 constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 320
 constexpr int PT_STRIDE = MAX_A + 1;   // floats per P^T row; odd => conflict-free row-per-lane stores
 constexpr int MAXT = 80;
-constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 2
+constexpr int F4_PER_ROW = KC / 4;                                             // float4 items per text row
+constexpr int B_ITEMS = (NPAD * F4_PER_ROW + TEXT_THREADS - 1) / TEXT_THREADS;  // 1
 
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
@@ -98,12 +102,12 @@ struct K1Smem {
   int sel[MAXT + 16];
   float rem[MAX_REM][NPAD];  // raw dot products of the remainder guide rows
   int pick_r, pick_i, flag;
-  uint64_t full_bar[2], empty_bar[2], done_bar;
+  uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
   uint32_t tmem_slot;
 };
 
 constexpr int K1_STAGE_AREA = 196608;  // two pipeline stages (73,728 B each at A <= 256); also holds P^T
-static_assert(K1_STAGE_AREA >= 2 * NPLANES * (TXT_TILE_BYTES + MAX_A * 64), "two stages at A = 384 must fit");
+static_assert(K1_STAGE_AREA >= 2 * NPLANES * (TXT_TILE_BYTES + MAX_A * ROW_B), "two stages at A = 384 must fit");
 static_assert(K1_STAGE_AREA >= MAXT * PT_STRIDE * 4, "the logits / P^T matrix aliases the stage area");
 constexpr int K1_SMEM_BYTES = 1024 + K1_STAGE_AREA + sizeof(K1Smem);
 
@@ -206,9 +210,9 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  // stage s: [text h][text m][text l][guide h: n_pad rows][guide m][guide l], 64 B rows
+  // stage s: [text h][text m][text l][guide h: n_pad rows][guide m][guide l], 32 B rows
   const int n_pad = a.n_pad;
-  const uint32_t g_plane = static_cast<uint32_t>(n_pad) * 64u;
+  const uint32_t g_plane = static_cast<uint32_t>(n_pad) * ROW_B;
   const uint32_t stage_bytes = NPLANES * (TXT_TILE_BYTES + g_plane);
   float* pt_full = reinterpret_cast<float*>(stage);  // [T][PT_STRIDE] logits, then probabilities
   float* pt = pt_full + PT_STRIDE;  // row r <-> text token r + 1 (header row dropped, guidance.py:55)
@@ -226,7 +230,7 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
 
   if (tid == 0) {
     for (int pl = 0; pl < NPLANES; ++pl) tma_prefetch_desc(&maps.m[pl][0]);
-    for (int st = 0; st < 2; ++st) {
+    for (int st = 0; st < MAX_STAGES; ++st) {
       mbar_init(&sm.full_bar[st], 1 + TEXT_WARPS);  // TMA expect_tx arrive + one arrive per text warp
       mbar_init(&sm.empty_bar[st], 1);
     }
@@ -260,7 +264,7 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
         for (int pl = 0; pl < NPLANES; ++pl) {
           tma_load_3d(gb + pl * g_plane, &maps.m[pl][0], &sm.full_bar[st], kc * KC, 0, g_idx);
           if (n_blk1 > 0)
-            tma_load_3d(gb + pl * g_plane + 256 * 64, &maps.m[pl][1], &sm.full_bar[st], kc * KC, 256, g_idx);
+            tma_load_3d(gb + pl * g_plane + 256 * ROW_B, &maps.m[pl][1], &sm.full_bar[st], kc * KC, 256, g_idx);
         }
       }
     }
@@ -279,15 +283,11 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
         const uint32_t tbase = smem_u32(stage + st * stage_bytes);
         const uint32_t gbase = tbase + NPLANES * TXT_TILE_BYTES;
 #pragma unroll
-        for (int ks = 0; ks < KC / 16; ++ks) {  // UMMA_K = 16 bf16 = 32 B = +2 in the desc
-#pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            const uint64_t td = umma_desc_sw64(tbase + pt_[q] * TXT_TILE_BYTES, 16, 512) + 2 * ks;
-            const uint64_t gd = umma_desc_sw64(gbase + pg_[q] * g_plane, 16, 512) + 2 * ks;
-            mma_f16_ss(tmem_base, td, gd, idesc0, (kc | ks | q) != 0);
-            if (n_blk1 > 0)
-              mma_f16_ss(tmem_base + 256, td, gd + ((256 * 64) >> 4), idesc1, (kc | ks | q) != 0);
-          }
+        for (int q = 0; q < 6; ++q) {  // one UMMA k-step (16 bf16 = the whole 32 B row) per chunk
+          const uint64_t td = umma_desc_sw32(tbase + pt_[q] * TXT_TILE_BYTES, 16, 256);
+          const uint64_t gd = umma_desc_sw32(gbase + pg_[q] * g_plane, 16, 256);
+          mma_f16_ss(tmem_base, td, gd, idesc0, (kc | q) != 0);
+          if (n_blk1 > 0) mma_f16_ss(tmem_base + 256, td, gd + ((256 * ROW_B) >> 4), idesc1, (kc | q) != 0);
         }
         tc_commit(&sm.empty_bar[st]);
       }
@@ -296,58 +296,52 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   } else {
     // ---- text warps: this prompt's chunk -> registers -> bf16 h / m / l split -> swizzled smem
     const int tt = tid - 64;
-    float4 rb[2][B_ITEMS];  // two chunks in flight
-    float ssb[B_ITEMS];
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
-    auto load_chunk = [&](int kc, float4 (&dst)[B_ITEMS]) {
-#pragma unroll
-      for (int j = 0; j < B_ITEMS; ++j) {
-        const int f = tt + j * TEXT_THREADS;
-        if (f < T * 8)
-          dst[j] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
-        else
-          dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    static_assert(B_ITEMS == 1, "one float4 per text thread and chunk");
+    float4 r0, r1, r2, r3;  // four chunks of this thread's float4 in flight (global latency ~ 2-3 chunks)
+    float ssb[B_ITEMS] = {0.f};
+    const int f = tt;
+    const int trow = f / F4_PER_ROW, tq = f % F4_PER_ROW;
+    auto load_chunk = [&](int kc) -> float4 {
+      if (f < T * F4_PER_ROW)
+        return __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(trow) * D + kc * KC) + tq);
+      return make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    load_chunk(0, rb[0]);
-    if (num_kc > 1) load_chunk(1, rb[1]);
+    r0 = load_chunk(0);
+    r1 = num_kc > 1 ? load_chunk(1) : r0;
+    r2 = num_kc > 2 ? load_chunk(2) : r0;
+    r3 = num_kc > 3 ? load_chunk(3) : r0;
+    const uint32_t toff = sw32_offset(trow, tq >> 1) + ((tq & 1) << 3);
     for (int kc = 0; kc < num_kc; ++kc) {
       const int st = kc % nst;
       mbar_wait(&sm.empty_bar[st], ((kc / nst) & 1) ^ 1);
       uint8_t* tb = stage + st * stage_bytes;
-#pragma unroll
-      for (int j = 0; j < B_ITEMS; ++j) {
-        const int f = tt + j * TEXT_THREADS;
-        if (f < NPAD * 8) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
-          const float4 v = (kc & 1) ? rb[1][j] : rb[0][j];
-          // float4 item q = f & 7 of row r covers elements 4q..4q+3 = bytes 8q..8q+7 of the 64 B row
-          const uint32_t off = sw64_offset(f >> 3, (f & 7) >> 1) + ((f & 1) << 3);
-          uint2 h, m, l;
-          split3_f4(v, h, m, l);
-          *reinterpret_cast<uint2*>(tb + off) = h;
-          *reinterpret_cast<uint2*>(tb + TXT_TILE_BYTES + off) = m;
-          *reinterpret_cast<uint2*>(tb + 2 * TXT_TILE_BYTES + off) = l;
-          ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        }
+      const int slot = kc & 3;
+      const float4 v = slot == 0 ? r0 : slot == 1 ? r1 : slot == 2 ? r2 : r3;
+      if (f < NPAD * F4_PER_ROW) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
+        uint2 h, m, l;
+        split3_f4(v, h, m, l);
+        *reinterpret_cast<uint2*>(tb + toff) = h;
+        *reinterpret_cast<uint2*>(tb + TXT_TILE_BYTES + toff) = m;
+        *reinterpret_cast<uint2*>(tb + 2 * TXT_TILE_BYTES + toff) = l;
+        ssb[0] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.full_bar[st]);
-      if (kc + 2 < num_kc) {  // refill the register buffer just consumed
-        if (kc & 1) load_chunk(kc + 2, rb[1]);
-        else load_chunk(kc + 2, rb[0]);
+      if (kc + 4 < num_kc) {  // refill the register slot just consumed
+        const float4 nv = load_chunk(kc + 4);
+        if (slot == 0) r0 = nv;
+        else if (slot == 1) r1 = nv;
+        else if (slot == 2) r2 = nv;
+        else r3 = nv;
       }
     }
-    // L2 norms of the text rows: the 8 threads that share a row sit in one aligned group of 8 lanes
-#pragma unroll
-    for (int j = 0; j < B_ITEMS; ++j) {
-      float ss = ssb[j];
+    // L2 norms of the text rows: the F4_PER_ROW (= 4) threads that share a row are adjacent lanes
+    {
+      float ss = ssb[0];
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-      const int f = tt + j * TEXT_THREADS;
-      if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
+      if (tq == 0 && trow < NPAD) sm.inv_norm_b[trow] = 1.0f / sqrtf(ss);
     }
     // remainder guide rows (A - a_mma <= 8) on the CUDA cores, exact fp32: warp w takes
     // text tokens w, w + 10, ...
@@ -849,7 +843,7 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
       uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(A) * D * 2};
       uint32_t box[3] = {KC, static_cast<uint32_t>(blk == 0 ? n_blk0 : (n_blk1 > 0 ? n_blk1 : 16)), 1};
       rc = encode_tmap(&maps.m[pl][blk], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, g_pl[pl], dims, strides, box,
-                       CU_TENSOR_MAP_SWIZZLE_64B);
+                       CU_TENSOR_MAP_SWIZZLE_32B);
       if (rc != FD_OK) return rc;
     }
   K1Args a;
@@ -857,7 +851,8 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   a.inv_norm_a = g_inv;
   a.a_mma = a_mma;
   a.n_pad = n_pad;
-  a.n_stages = (2 * NPLANES * (TXT_TILE_BYTES + n_pad * 64) <= K1_STAGE_AREA) ? 2 : 1;
+  a.n_stages = K1_STAGE_AREA / (NPLANES * (TXT_TILE_BYTES + n_pad * ROW_B));
+  if (a.n_stages > MAX_STAGES) a.n_stages = MAX_STAGES;
   a.text = text_dev;
   a.guide = guide_dev;
   a.n_text = n_text;

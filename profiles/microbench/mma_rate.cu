@@ -42,6 +42,38 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
     long long t1 = clock64();
     out[blockIdx.x] = t1 - t0;
   }
+  __syncthreads();
+  tc_fence_after();
+  // TMEM read-back cost: 256 columns per lane, (a) wait after every x16 load, (b) 4 loads per wait
+  {
+    const uint32_t lane_addr = static_cast<uint32_t>((threadIdx.x >> 5) * 32) << 16;
+    float acc = 0.f;
+    long long ta = clock64();
+    for (int c = 0; c < 256; c += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(tmem + lane_addr + c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 16; ++q) acc += __uint_as_float(v[q]);
+    }
+    long long tb = clock64();
+    for (int c = 0; c < 256; c += 64) {
+      uint32_t v[4][16];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) tmem_ld_x16(tmem + lane_addr + c + 16 * g, v[g]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc += __uint_as_float(v[g][q]);
+    }
+    long long tc = clock64();
+    if (threadIdx.x == 0) {
+      out[148 + blockIdx.x] = tb - ta;
+      out[296 + blockIdx.x] = tc - tb;
+    }
+    if (acc == 123.456f) out[0] = 0;
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) { tc_fence_after(); tmem_dealloc(tmem, 256); }
@@ -49,7 +81,7 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int iters, int 
 
 int main() {
   long long* d;
-  cudaMalloc(&d, 148 * sizeof(long long));
+  cudaMalloc(&d, 3 * 148 * sizeof(long long));
   const int smem = (128 + 256) * 128 * 4 + 1024;
   cudaFuncSetAttribute(mma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaFuncSetAttribute(mma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -62,13 +94,14 @@ int main() {
           else mma_rate_kernel<false><<<grid, 128, smem>>>(N, iters, 4, d);
           cudaDeviceSynchronize();
         }
-        long long h[148];
-        cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long h[444];
+        cudaMemcpy(h, d, 444 * sizeof(long long), cudaMemcpyDeviceToHost);
         long long mx = 0;
         for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
         printf("grid=%3d kind=%s M=128 N=%3d K=%2d : %7.1f cycles per MMA (%d MMAs)  err=%s\n", grid,
                tf32 ? "tf32" : "bf16", N, tf32 ? 8 : 16, double(mx) / (iters * 4), iters * 4,
                cudaGetErrorString(cudaGetLastError()));
+        printf("      tmem read-back of 256 cols: wait-each %lld cycles, 4-per-wait %lld cycles\n", h[148], h[296]);
       }
   return 0;
 }
