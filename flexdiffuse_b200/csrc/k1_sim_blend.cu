@@ -8,20 +8,19 @@
 //   guidance.py:215-272  Tweener.tween
 // Algorithm spec: SURVEY.md 3.6 (verified bit-level against the reference by the oracle tests).
 //
-// A tiny prep kernel splits the (usually shared) guide once into three bf16 planes (hi / mid / lo,
-// 24 mantissa bits) and its inverse L2 norms.  One CTA of the main kernel (384 threads, 1 CTA / SM):
-//   1. GEMM  D[j,i] = <text_j, guide_i>  (M = 128 lanes of which T<=80 used, N = A<=384, K = D) on
-//      tcgen05 kind::f16 (bf16) with a 6-product split  h.h + (h.m + m.h) + (m.m + h.l + l.h)  so
-//      the logits are fp32-equivalent (a single bf16/tf32 pass flips arg-max / threshold
-//      decisions).  v3 used 3 tf32 products; tf32 UMMA measured ~4x slower per MAC
-//      than bf16 on this part (profiles/r01/SUMMARY.md), so 6 bf16 products are ~2.5x cheaper.
-//      Warp-specialised pipeline over K chunks of 16 (one UMMA k-step, SWIZZLE_32B rows), up to 6
-//      stages in flight (a 2-stage version was bound by the TMA round trip): warp 0 TMA-loads the
-//      guide planes, warps 2-11 split the prompt's own chunk in registers into the same layout
-//      (+ sum of squares for its L2 norms, two chunks prefetched), warp 1 issues the MMAs.  Guide
-//      rows past the last multiple of 16 (the 257th CLIP token) are <= 8 dot products per text
-//      token and go to the CUDA cores in exact fp32.
+// A tiny prep kernel splits the (usually shared) guide once into tf32 hi / lo planes and its inverse
+// L2 norms.  Structure of one CTA of the main kernel (384 threads, 1 CTA / SM):
+//   1. GEMM  D[i,j] = <guide_i, text_j>  (A<=384 x T<=80 x D) on tcgen05, kind::tf32 with the
+//      3-pass hi/lo split (hi*hi + lo*hi + hi*lo) so the logits are fp32-equivalent
+//      (a single bf16/tf32 pass flips arg-max / threshold decisions).
+//      Warp-specialised 2-stage pipeline over K chunks of 32: warp 0 TMA-loads the guide hi / lo
+//      tiles (SWIZZLE_128B), warps 2-11 split the prompt's own chunk in registers into the same
+//      layout (+ sum of squares for its L2 norms), warp 1 issues the MMAs.  Guide rows beyond the
+//      last full 128-row tile (the 257th CLIP token) are <= 8 dot products per text token and go
+//      to the CUDA cores instead of wasting a third MMA tile.
 //      Accumulator: 128 lanes (text tokens) x up to 384 columns (guide tokens) in TMEM.
+//      (Tried and measured slower on B200, see git history / profiles/r01/SUMMARY.md: a 6-product
+//      bf16 hi/mid/lo split with SWIZZLE_64B or SWIZZLE_32B chunks and up to 5 stages.)
 //   2. Softmax over the text tokens: one thread per TMEM lane (= guide token), no shuffles.
 //      P^T is parked in shared memory (aliasing the operand staging area).
 //   3. Column arg-max / greedy no-reuse assignment / direct mapping: warp-shuffle reductions.
@@ -38,19 +37,15 @@ constexpr int K1_THREADS = 384;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int NPAD = 80;          // UMMA N (text tokens padded)
 constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
-constexpr int KC = 16;            // elements per K chunk = one UMMA k-step (32 B bf16 swizzle row)
-constexpr int ROW_B = KC * 2;     // bytes per operand row in shared memory
-constexpr int MAX_STAGES = 6;
-constexpr int TXT_TILE_BYTES = 128 * ROW_B;  // M operand plane: 128 rows (80 used) x 32 B; 3 planes
-constexpr int NPLANES = 3;
+constexpr int KC = 32;            // fp32 per K chunk (one 128 B swizzle row)
+constexpr int TXT_TILE_BYTES = 128 * 128;  // M operand: 128 rows (80 used) x 128 B, hi and lo
 constexpr int MAX_A = MAX_TILES * 128;     // 384 guide tokens
 constexpr int MAX_REM = 8;        // guide rows past the last multiple of 16 that go to the CUDA cores
 constexpr int TEXT_WARPS = K1_WARPS - 2;
 constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 320
 constexpr int PT_STRIDE = MAX_A + 1;   // floats per P^T row; odd => conflict-free row-per-lane stores
 constexpr int MAXT = 80;
-constexpr int F4_PER_ROW = KC / 4;                                             // float4 items per text row
-constexpr int B_ITEMS = (NPAD * F4_PER_ROW + TEXT_THREADS - 1) / TEXT_THREADS;  // 1
+constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 2
 
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
@@ -83,11 +78,6 @@ struct K1Args {
   float* sim;
 };
 
-// tensor maps of the three guide planes: [plane][column block 0 (<=256 rows) / block 1]
-struct K1Maps {
-  CUtensorMap m[NPLANES][2];
-};
-
 struct K1Smem {
   // staging / P^T area comes first (1024-aligned), then this struct
   float inv_norm_a[MAX_TILES * 128];
@@ -102,12 +92,12 @@ struct K1Smem {
   int sel[MAXT + 16];
   float rem[MAX_REM][NPAD];  // raw dot products of the remainder guide rows
   int pick_r, pick_i, flag;
-  uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], done_bar;
+  uint64_t full_bar[2], empty_bar[2], done_bar;
   uint32_t tmem_slot;
 };
 
-constexpr int K1_STAGE_AREA = 196608;  // two pipeline stages (73,728 B each at A <= 256); also holds P^T
-static_assert(K1_STAGE_AREA >= 2 * NPLANES * (TXT_TILE_BYTES + MAX_A * ROW_B), "two stages at A = 384 must fit");
+constexpr int K1_STAGE_AREA = 2 * (2 * TXT_TILE_BYTES + 2 * 256 * 128);  // 196,608: two stages at A <= 256
+static_assert(K1_STAGE_AREA >= 2 * TXT_TILE_BYTES + 2 * MAX_A * 128, "one stage at A = 384 must fit");
 static_assert(K1_STAGE_AREA >= MAXT * PT_STRIDE * 4, "the logits / P^T matrix aliases the stage area");
 constexpr int K1_SMEM_BYTES = 1024 + K1_STAGE_AREA + sizeof(K1Smem);
 
@@ -158,46 +148,27 @@ __device__ __forceinline__ int warp_consume_all_unused(unsigned int* used, int A
   return hi;
 }
 
-// fp32 -> three bf16 planes: h = bf16(x), m = bf16(x - h), l = bf16(x - h - m)  (24 mantissa bits)
-__device__ __forceinline__ void split3(float x, __nv_bfloat16& h, __nv_bfloat16& m, __nv_bfloat16& l) {
-  h = __float2bfloat16_rn(x);
-  const float r1 = x - __bfloat162float(h);
-  m = __float2bfloat16_rn(r1);
-  l = __float2bfloat16_rn(r1 - __bfloat162float(m));
-}
-__device__ __forceinline__ void split3_f4(const float4& v, uint2& h, uint2& m, uint2& l) {
-  __nv_bfloat16 hh[4], mm[4], ll[4];
-  split3(v.x, hh[0], mm[0], ll[0]);
-  split3(v.y, hh[1], mm[1], ll[1]);
-  split3(v.z, hh[2], mm[2], ll[2]);
-  split3(v.w, hh[3], mm[3], ll[3]);
-  auto pack = [](const __nv_bfloat16* a) {
-    uint2 r;
-    r.x = static_cast<uint32_t>(__bfloat16_as_ushort(a[0])) | (static_cast<uint32_t>(__bfloat16_as_ushort(a[1])) << 16);
-    r.y = static_cast<uint32_t>(__bfloat16_as_ushort(a[2])) | (static_cast<uint32_t>(__bfloat16_as_ushort(a[3])) << 16);
-    return r;
-  };
-  h = pack(hh);
-  m = pack(mm);
-  l = pack(ll);
-}
-
-// guide fp32 -> bf16 hi / mid / lo planes and 1 / |row|.  One warp per row.
-__global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ ph,
-                                                            __nv_bfloat16* __restrict__ pm,
-                                                            __nv_bfloat16* __restrict__ pl,
-                                                            float* __restrict__ inv_norm, int rows, int D) {
+// guide fp32 -> tf32 hi plane, lo plane (x - hi, exact in fp32) and 1 / |row|.  One warp per row.
+__global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, float* __restrict__ hi,
+                                                            float* __restrict__ lo, float* __restrict__ inv_norm,
+                                                            int rows, int D) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
   float ss = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
     const float4 v = *reinterpret_cast<const float4*>(g + static_cast<size_t>(row) * D + c);
-    uint2 h, m, l;
-    split3_f4(v, h, m, l);
-    *reinterpret_cast<uint2*>(ph + static_cast<size_t>(row) * D + c) = h;
-    *reinterpret_cast<uint2*>(pm + static_cast<size_t>(row) * D + c) = m;
-    *reinterpret_cast<uint2*>(pl + static_cast<size_t>(row) * D + c) = l;
+    float4 h, l;
+    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+    l.x = v.x - h.x;
+    l.y = v.y - h.y;
+    l.z = v.z - h.z;
+    l.w = v.w - h.w;
+    *reinterpret_cast<float4*>(hi + static_cast<size_t>(row) * D + c) = h;
+    *reinterpret_cast<float4*>(lo + static_cast<size_t>(row) * D + c) = l;
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
 #pragma unroll
@@ -206,14 +177,16 @@ __global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restr
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 1)
-k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
+k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                    const __grid_constant__ CUtensorMap tm_hi2, const __grid_constant__ CUtensorMap tm_lo2,
+                    const K1Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  // stage s: [text h][text m][text l][guide h: n_pad rows][guide m][guide l], 32 B rows
+  // stage s: [text hi][text lo][guide hi: n_pad rows][guide lo: n_pad rows]
   const int n_pad = a.n_pad;
-  const uint32_t g_plane = static_cast<uint32_t>(n_pad) * ROW_B;
-  const uint32_t stage_bytes = NPLANES * (TXT_TILE_BYTES + g_plane);
+  const uint32_t g_plane = static_cast<uint32_t>(n_pad) * 128u;
+  const uint32_t stage_bytes = 2u * TXT_TILE_BYTES + 2u * g_plane;
   float* pt_full = reinterpret_cast<float*>(stage);  // [T][PT_STRIDE] logits, then probabilities
   float* pt = pt_full + PT_STRIDE;  // row r <-> text token r + 1 (header row dropped, guidance.py:55)
   K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + K1_STAGE_AREA);
@@ -229,8 +202,9 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   const uint32_t tmem_cols = n_pad <= 256 ? 256 : 512;  // lane = text token, column = guide token
 
   if (tid == 0) {
-    for (int pl = 0; pl < NPLANES; ++pl) tma_prefetch_desc(&maps.m[pl][0]);
-    for (int st = 0; st < MAX_STAGES; ++st) {
+    tma_prefetch_desc(&tm_hi);
+    tma_prefetch_desc(&tm_lo);
+    for (int st = 0; st < 2; ++st) {
       mbar_init(&sm.full_bar[st], 1 + TEXT_WARPS);  // TMA expect_tx arrive + one arrive per text warp
       mbar_init(&sm.empty_bar[st], 1);
     }
@@ -253,95 +227,113 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
   const int g_idx = a.guide_batch == 1 ? 0 : b_idx;
   const int n_blk0 = min(n_pad, 256), n_blk1 = n_pad - n_blk0;  // UMMA N of the one or two column blocks
   if (warp == 0) {
-    // ---- TMA producer: the three guide planes of every K chunk
+    // ---- TMA producer: guide hi / lo rows of every K chunk
     if (elect_one()) {
       for (int kc = 0; kc < num_kc; ++kc) {
         const int st = kc % nst;
         const uint32_t ph = (kc / nst) & 1;
         mbar_wait_backoff(&sm.empty_bar[st], ph ^ 1);
-        mbar_expect_tx(&sm.full_bar[st], NPLANES * g_plane);
-        uint8_t* gb = stage + st * stage_bytes + NPLANES * TXT_TILE_BYTES;
-        for (int pl = 0; pl < NPLANES; ++pl) {
-          tma_load_3d(gb + pl * g_plane, &maps.m[pl][0], &sm.full_bar[st], kc * KC, 0, g_idx);
-          if (n_blk1 > 0)
-            tma_load_3d(gb + pl * g_plane + 256 * ROW_B, &maps.m[pl][1], &sm.full_bar[st], kc * KC, 256, g_idx);
+        mbar_expect_tx(&sm.full_bar[st], 2u * g_plane);
+        uint8_t* gb_hi = stage + st * stage_bytes + 2 * TXT_TILE_BYTES;
+        uint8_t* gb_lo = gb_hi + g_plane;
+        tma_load_3d(gb_hi, &tm_hi, &sm.full_bar[st], kc * KC, 0, g_idx);
+        tma_load_3d(gb_lo, &tm_lo, &sm.full_bar[st], kc * KC, 0, g_idx);
+        if (n_blk1 > 0) {
+          tma_load_3d(gb_hi + 256 * 128, &tm_hi2, &sm.full_bar[st], kc * KC, 256, g_idx);
+          tma_load_3d(gb_lo + 256 * 128, &tm_lo2, &sm.full_bar[st], kc * KC, 256, g_idx);
         }
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: D[text j, guide i] += text(128 x 16) . guide(N x 16)^T, six bf16 products,
-    //      smallest terms first
+    // ---- MMA issuer: D[text j, guide i] += text(128 x 8) . guide(N x 8)^T, three tf32 products
     if (elect_one()) {
-      const uint32_t idesc0 = umma_idesc(UMMA_BF16, 128, n_blk0, 0, 0);
-      const uint32_t idesc1 = umma_idesc(UMMA_BF16, 128, n_blk1 > 0 ? n_blk1 : 16, 0, 0);
-      // (text plane, guide plane): h=0 m=1 l=2
-      const int pt_[6] = {2, 0, 1, 1, 0, 0}, pg_[6] = {0, 2, 1, 0, 1, 0};
+      const uint32_t idesc0 = umma_idesc(UMMA_TF32, 128, n_blk0, 0, 0);
+      const uint32_t idesc1 = umma_idesc(UMMA_TF32, 128, n_blk1 > 0 ? n_blk1 : 16, 0, 0);
       for (int kc = 0; kc < num_kc; ++kc) {
         const int st = kc % nst;
         mbar_wait_backoff(&sm.full_bar[st], (kc / nst) & 1);
         tc_fence_after();
-        const uint32_t tbase = smem_u32(stage + st * stage_bytes);
-        const uint32_t gbase = tbase + NPLANES * TXT_TILE_BYTES;
+        uint8_t* base = stage + st * stage_bytes;
+        const uint64_t th = umma_desc_sw128(smem_u32(base), 16, 1024);
+        const uint64_t tl = umma_desc_sw128(smem_u32(base + TXT_TILE_BYTES), 16, 1024);
+        const uint64_t gh = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES), 16, 1024);
+        const uint64_t gl = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES + g_plane), 16, 1024);
 #pragma unroll
-        for (int q = 0; q < 6; ++q) {  // one UMMA k-step (16 bf16 = the whole 32 B row) per chunk
-          const uint64_t td = umma_desc_sw32(tbase + pt_[q] * TXT_TILE_BYTES, 16, 256);
-          const uint64_t gd = umma_desc_sw32(gbase + pg_[q] * g_plane, 16, 256);
-          mma_f16_ss(tmem_base, td, gd, idesc0, (kc | q) != 0);
-          if (n_blk1 > 0) mma_f16_ss(tmem_base + 256, td, gd + ((256 * ROW_B) >> 4), idesc1, (kc | q) != 0);
+        for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
+          mma_tf32_ss(tmem_base, tl + 2 * ks, gh + 2 * ks, idesc0, (kc | ks) != 0);  // small terms first
+          mma_tf32_ss(tmem_base, th + 2 * ks, gl + 2 * ks, idesc0, 1);
+          mma_tf32_ss(tmem_base, th + 2 * ks, gh + 2 * ks, idesc0, 1);
+        }
+        if (n_blk1 > 0) {
+          const uint64_t gh2 = gh + ((256 * 128) >> 4), gl2 = gl + ((256 * 128) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            mma_tf32_ss(tmem_base + 256, tl + 2 * ks, gh2 + 2 * ks, idesc1, (kc | ks) != 0);
+            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gl2 + 2 * ks, idesc1, 1);
+            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gh2 + 2 * ks, idesc1, 1);
+          }
         }
         tc_commit(&sm.empty_bar[st]);
       }
       tc_commit(&sm.done_bar);
     }
   } else {
-    // ---- text warps: this prompt's chunk -> registers -> bf16 h / m / l split -> swizzled smem
+    // ---- text warps: this prompt's chunk -> registers -> hi / lo split -> swizzled smem
     const int tt = tid - 64;
-    static_assert(B_ITEMS == 1, "one float4 per text thread and chunk");
-    float4 r0, r1, r2, r3;  // four chunks of this thread's float4 in flight (global latency ~ 2-3 chunks)
-    float ssb[B_ITEMS] = {0.f};
-    const int f = tt;
-    const int trow = f / F4_PER_ROW, tq = f % F4_PER_ROW;
-    auto load_chunk = [&](int kc) -> float4 {
-      if (f < T * F4_PER_ROW)
-        return __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(trow) * D + kc * KC) + tq);
-      return make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 rb[B_ITEMS];
+    float ssb[B_ITEMS];
+#pragma unroll
+    for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
+    auto load_chunk = [&](int kc) {
+#pragma unroll
+      for (int j = 0; j < B_ITEMS; ++j) {
+        const int f = tt + j * TEXT_THREADS;
+        if (f < T * 8)
+          rb[j] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
+        else
+          rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     };
-    r0 = load_chunk(0);
-    r1 = num_kc > 1 ? load_chunk(1) : r0;
-    r2 = num_kc > 2 ? load_chunk(2) : r0;
-    r3 = num_kc > 3 ? load_chunk(3) : r0;
-    const uint32_t toff = sw32_offset(trow, tq >> 1) + ((tq & 1) << 3);
+    load_chunk(0);
     for (int kc = 0; kc < num_kc; ++kc) {
       const int st = kc % nst;
       mbar_wait(&sm.empty_bar[st], ((kc / nst) & 1) ^ 1);
-      uint8_t* tb = stage + st * stage_bytes;
-      const int slot = kc & 3;
-      const float4 v = slot == 0 ? r0 : slot == 1 ? r1 : slot == 2 ? r2 : r3;
-      if (f < NPAD * F4_PER_ROW) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
-        uint2 h, m, l;
-        split3_f4(v, h, m, l);
-        *reinterpret_cast<uint2*>(tb + toff) = h;
-        *reinterpret_cast<uint2*>(tb + TXT_TILE_BYTES + toff) = m;
-        *reinterpret_cast<uint2*>(tb + 2 * TXT_TILE_BYTES + toff) = l;
-        ssb[0] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      uint8_t* t_hi = stage + st * stage_bytes;
+      uint8_t* t_lo = t_hi + TXT_TILE_BYTES;
+#pragma unroll
+      for (int j = 0; j < B_ITEMS; ++j) {
+        const int f = tt + j * TEXT_THREADS;
+        if (f < NPAD * 8) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
+          const float4 v = rb[j];
+          const uint32_t off = sw128_offset(f >> 3, f & 7);
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+          l.x = v.x - h.x;
+          l.y = v.y - h.y;
+          l.z = v.z - h.z;
+          l.w = v.w - h.w;
+          *reinterpret_cast<float4*>(t_hi + off) = h;
+          *reinterpret_cast<float4*>(t_lo + off) = l;
+          ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.full_bar[st]);
-      if (kc + 4 < num_kc) {  // refill the register slot just consumed
-        const float4 nv = load_chunk(kc + 4);
-        if (slot == 0) r0 = nv;
-        else if (slot == 1) r1 = nv;
-        else if (slot == 2) r2 = nv;
-        else r3 = nv;
-      }
+      if (kc + 1 < num_kc) load_chunk(kc + 1);  // in flight while the MMAs of this chunk run
     }
-    // L2 norms of the text rows: the F4_PER_ROW (= 4) threads that share a row are adjacent lanes
-    {
-      float ss = ssb[0];
+    // L2 norms of the text rows: the 8 threads that share a row sit in one aligned group of 8 lanes
+#pragma unroll
+    for (int j = 0; j < B_ITEMS; ++j) {
+      float ss = ssb[j];
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      if (tq == 0 && trow < NPAD) sm.inv_norm_b[trow] = 1.0f / sqrtf(ss);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      const int f = tt + j * TEXT_THREADS;
+      if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
     }
     // remainder guide rows (A - a_mma <= 8) on the CUDA cores, exact fp32: warp w takes
     // text tokens w, w + 10, ...
@@ -791,7 +783,7 @@ k1_sim_blend_kernel(const __grid_constant__ K1Maps maps, const K1Args a) {
 }  // namespace fd
 
 extern "C" int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D) {
-  return 3 * static_cast<int64_t>(guide_batch) * A * D * 2 + static_cast<int64_t>(guide_batch) * A * 4 + 64;
+  return (2 * static_cast<int64_t>(guide_batch) * A * D + static_cast<int64_t>(guide_batch) * A) * 4 + 64;
 }
 
 // development aid (not part of the product ABI): device buffer of >= 8 int64 for phase timestamps
@@ -816,18 +808,18 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   int rc = check_device();
   if (rc != FD_OK) return rc;
 
-  // workspace: [guide h plane][m plane][l plane] (bf16) [inverse norms] (fp32)
+  // workspace: [guide hi plane][guide lo plane][inverse norms]
   const int64_t plane = static_cast<int64_t>(guide_batch) * A * D;
   FD_REQUIRE(workspace_dev && workspace_bytes >= fd_sim_blend_workspace_bytes(guide_batch, A, D),
              "fd_sim_blend: workspace too small (need fd_sim_blend_workspace_bytes)");
   FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0, "fd_sim_blend: workspace must be 16-byte aligned");
-  __nv_bfloat16* g_pl[NPLANES];
-  for (int pl = 0; pl < NPLANES; ++pl) g_pl[pl] = static_cast<__nv_bfloat16*>(workspace_dev) + pl * plane;
-  float* g_inv = reinterpret_cast<float*>(static_cast<char*>(workspace_dev) + ((NPLANES * plane * 2 + 15) / 16) * 16);
+  float* g_hi = static_cast<float*>(workspace_dev);
+  float* g_lo = g_hi + plane;
+  float* g_inv = g_lo + plane;
   cudaStream_t cst = static_cast<cudaStream_t>(stream);
   {
     const int rows = guide_batch * A;
-    k1_prep_guide_kernel<<<(rows + 7) / 8, 256, 0, cst>>>(guide_dev, g_pl[0], g_pl[1], g_pl[2], g_inv, rows, D);
+    k1_prep_guide_kernel<<<(rows + 7) / 8, 256, 0, cst>>>(guide_dev, g_hi, g_lo, g_inv, rows, D);
     FD_CUDA_OK(cudaGetLastError());
   }
   // rows handled by the tensor cores: everything except a short (<= MAX_REM) tail past a multiple of 16
@@ -835,24 +827,23 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   const int a_mma = (rem != 0 && rem <= MAX_REM && A > 16) ? A - rem : A;
   const int n_pad = (a_mma + 15) / 16 * 16;
   const int n_blk0 = n_pad < 256 ? n_pad : 256, n_blk1 = n_pad - n_blk0;
-  K1Maps maps;
-  for (int pl = 0; pl < NPLANES; ++pl)
-    for (int blk = 0; blk < 2; ++blk) {
-      // rows >= a_mma of a box are never used: keep them out of the map so TMA zero-fills them
-      uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), static_cast<uint64_t>(guide_batch)};
-      uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(A) * D * 2};
-      uint32_t box[3] = {KC, static_cast<uint32_t>(blk == 0 ? n_blk0 : (n_blk1 > 0 ? n_blk1 : 16)), 1};
-      rc = encode_tmap(&maps.m[pl][blk], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, g_pl[pl], dims, strides, box,
-                       CU_TENSOR_MAP_SWIZZLE_32B);
-      if (rc != FD_OK) return rc;
-    }
+  CUtensorMap tm_hi, tm_lo, tm_hi2, tm_lo2;
+  for (int which = 0; which < 4; ++which) {
+    // rows >= a_mma of a box are never used: keep them out of the map so TMA zero-fills them
+    uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), static_cast<uint64_t>(guide_batch)};
+    uint64_t strides[2] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(A) * D * 4};
+    uint32_t box[3] = {KC, static_cast<uint32_t>(which < 2 ? n_blk0 : (n_blk1 > 0 ? n_blk1 : 16)), 1};
+    CUtensorMap* dst = which == 0 ? &tm_hi : which == 1 ? &tm_lo : which == 2 ? &tm_hi2 : &tm_lo2;
+    rc = encode_tmap(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (which & 1) ? g_lo : g_hi, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+  }
   K1Args a;
   a.timing = g_k1_timing;
   a.inv_norm_a = g_inv;
   a.a_mma = a_mma;
   a.n_pad = n_pad;
-  a.n_stages = K1_STAGE_AREA / (NPLANES * (TXT_TILE_BYTES + n_pad * ROW_B));
-  if (a.n_stages > MAX_STAGES) a.n_stages = MAX_STAGES;
+  a.n_stages = (2 * (2 * TXT_TILE_BYTES + 2 * n_pad * 128) <= K1_STAGE_AREA) ? 2 : 1;
   a.text = text_dev;
   a.guide = guide_dev;
   a.n_text = n_text;
@@ -881,7 +872,7 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   FD_REQUIRE(chunks <= 65535, "fd_sim_blend: too many parameter chunks");
   FD_CUDA_OK(cudaFuncSetAttribute(k1_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
   dim3 grid(n_text, chunks);
-  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(maps, a);
+  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(tm_hi, tm_lo, tm_hi2, tm_lo2, a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }
