@@ -283,6 +283,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-kernels', action='store_true', help='skip kernel microbenches')
+    ap.add_argument('--batch', type=int, default=1,
+                    help='images per step per GPU (default 1 = BASELINE.json configs[1])')
     ap.add_argument('--kernels-only', action='store_true',
                     help='development aid: only the kernel roofline section')
     args = ap.parse_args()
@@ -324,7 +326,7 @@ def main():
         print(json.dumps(kernel_rooflines(dev, unet, peaks)))
         return
     vae = factory.build_vae(dev, torch.bfloat16, seed=1)
-    B = 1
+    B = args.batch
     g = torch.Generator().manual_seed(1234 + rank)
     h_uncond = torch.randn(1, 77, 768, generator=g).pin_memory()
     h_embeds = torch.randn(B, 77, 768, generator=g).pin_memory()
@@ -407,7 +409,8 @@ def main():
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': W, 'ms_per_step': ms_res, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'images_per_step_per_gpu': B,
+        'config': {'workload': WORKLOAD if B == 1 else WORKLOAD.replace('batch 1 per GPU', f'batch {B} per GPU'),
+                   'images_per_step_per_gpu': B,
                    'parallelism': f'replicas x{world}: independent samples sharded over ranks, no '
                                   'collective in the loop, one NCCL all-gather of the output '
                                   'latents per step',
@@ -421,7 +424,7 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
     }
-    if rank == 0 and world == 1 and not args.no_kernels:
+    if rank == 0 and world == 1 and not args.no_kernels and B == 1:
         kr = kernel_rooflines(dev, unet, peaks)
         line['roofline'] = kr['k3']
         line['roofline_k4'] = kr['k4']
