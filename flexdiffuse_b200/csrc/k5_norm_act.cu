@@ -8,13 +8,16 @@
 //
 //   K5  y = act( GroupNorm( x + bias[n,c] ) * gamma[c] + beta[c] )        NHWC bf16 in / out
 //       diffusers ResnetBlock2D: norm1 -> SiLU, (+ time_emb_proj) -> norm2 -> SiLU;
-//       SpatialTransformer.norm, conv_norm_out.  Two launches: per-slab partial (sum, sumsq) per
-//       channel pair (the last CTA of a sample reduces them to mean / rstd), then normalise + affine +
-//       SiLU: two launches, fixed summation order (bit-reproducible).
+//       SpatialTransformer.norm, conv_norm_out.  Small (latency-bound) activations: ONE launch, a
+//       thread-block cluster per (sample, group) with the slab resident in shared memory and the
+//       statistics exchanged over DSMEM.  Large activations (batches, the VAE): three streaming
+//       launches (stats / finalize / apply) with 16-byte row-coalesced accesses.  Fixed summation
+//       order everywhere (bit-reproducible).
 //   K7  y = x + h + bias[c]: the resnet residual add with conv2's bias folded in (cuDNN would
 //       otherwise add every convolution bias with a separate broadcast kernel).
 //   K6  out[m, f] = in[m, f] * gelu(in[m, F + f])                          diffusers GEGLU
 #include <math.h>
+#include <stdlib.h>
 
 #include "fd_common.cuh"
 
@@ -23,150 +26,164 @@ namespace {
 
 constexpr int GN_THREADS = 256;   // 8 warps: warp w takes rows w, w+8, ... of the slab
 constexpr int GN_WARPS = GN_THREADS / 32;
-constexpr int GN_ROWS = 32;        // rows (pixels) per CTA in the apply phase
-constexpr int GN_STAT_ROWS = 128;  // rows per CTA in the statistics phase
 constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_VEC_MAX_SLABS = 512;               // streaming path: slabs per sample
+constexpr int64_t GN_CLUSTER_MAX_BYTES = 12 << 20;  // larger activations take the streaming path
 constexpr int GN_MAX_CG2 = 64;     // channel pairs per group on the cluster path (C/G <= 128)
-
-struct GnArgs {
-  const __nv_bfloat16* x;      // [N, HW, C] (channels_last view of [N, C, H, W])
-  const __nv_bfloat16* bias;   // [N, C] (row stride bias_stride elements) or nullptr
-  int64_t bias_stride;
-  const __nv_bfloat16* gamma;  // [C]
-  const __nv_bfloat16* beta;   // [C]
-  float2* partial;             // [N, slabs, C/2]  per channel-pair (sum, sumsq) of one slab
-  float2* stats;               // [N, G]           (mean, rstd)
-  int* counter;                // [N] ticket counters (zero between launches)
-  __nv_bfloat16* y;            // [N, HW, C]
-  int HW, C, G, slabs, stat_slabs;
-  float eps;
-  int act_silu;
-};
 
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
   return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
 }
 
-// phase 1 + 2.  grid (C/64, stat_slabs, N): one CTA = 32 channel pairs x 128 rows; a warp reads 128
-// contiguous bytes per row, 8 rows in flight per thread.  The LAST CTA of a sample to finish
-// (ticket counter, self-resetting) reduces that sample's partials to (mean, rstd) per group, so
-// no separate finalise launch is needed.  Every reduction has a fixed order: bit-reproducible.
-__global__ void __launch_bounds__(GN_THREADS) k5_gn_stats_kernel(const GnArgs a) {
-  __shared__ float2 red[GN_WARPS][32];
-  __shared__ int s_last;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pairs = a.C >> 1;
-  const int p = blockIdx.x * 32 + lane;
-  const int slab = blockIdx.y, n = blockIdx.z;
-  const int r0 = slab * GN_STAT_ROWS;
-  const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + static_cast<size_t>(n) * a.HW * pairs + p;
-  float2 b = make_float2(0.f, 0.f);
-  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[p]);
-  float s = 0.f, q = 0.f;
+// ---- streaming path for large activations (batches > 1, the VAE): three launches, every global
+// access a 16-byte vector over full rows.  A thread owns a fixed column of 8 channels (so its
+// gamma / beta / bias live in registers) and walks down the rows of its slab.
+//   stats    : grid (slabs, N), block (C/8, ty): per-slab, per-group (sum, sumsq) partials
+//   finalize : grid (G, N): partials -> (mean, rstd), fixed order
+//   apply    : same mapping as stats
+struct GnVecArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* bias;
+  int64_t bias_stride;
+  const __nv_bfloat16* gamma;
+  const __nv_bfloat16* beta;
+  float2* partial;  // [N, GN_VEC_MAX_SLABS, G]
+  float2* stats;    // [N, G]
+  __nv_bfloat16* y;
+  int HW, C, G, slabs, rows_per_slab;
+  float eps;
+  int act_silu;
+};
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
-    uint32_t v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + warp + (half * 8 + i) * GN_WARPS;
-      v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = r0 + warp + (half * 8 + i) * GN_WARPS;
-      if (r < a.HW) {
-        float2 f = bf2_to_f2(v[i]);
-        f.x += b.x;
-        f.y += b.y;
-        s += f.x + f.y;
-        q += f.x * f.x + f.y * f.y;
-      }
-    }
+  for (int k = 0; k < 4; ++k) {
+    f[2 * k] = __uint_as_float(w[k] << 16);
+    f[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
   }
-  red[warp][lane] = make_float2(s, q);
-  __syncthreads();
-  if (warp == 0) {
-    float2 t = red[0][lane];
-#pragma unroll
-    for (int w = 1; w < GN_WARPS; ++w) {
-      t.x += red[w][lane].x;
-      t.y += red[w][lane].y;
-    }
-    a.partial[(static_cast<size_t>(n) * a.stat_slabs + slab) * pairs + p] = t;
-  }
-  // ---- last CTA of this sample finalises
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int ticket = atomicAdd(&a.counter[n], 1);
-    s_last = ticket == static_cast<int>(gridDim.x * gridDim.y) - 1;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int cg2 = (a.C / a.G) >> 1;
-  const int total = a.stat_slabs * cg2;
-  const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
-  for (int g = warp; g < a.G; g += GN_WARPS) {
-    float ss = 0.f, qq = 0.f;
-    for (int i = lane; i < total; i += 32) {
-      const int sl = i / cg2, k = i - sl * cg2;
-      const float2 t = __ldcg(&a.partial[(static_cast<size_t>(n) * a.stat_slabs + sl) * pairs + g * cg2 + k]);
-      ss += t.x;
-      qq += t.y;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ss += __shfl_xor_sync(0xffffffffu, ss, o);
-      qq += __shfl_xor_sync(0xffffffffu, qq, o);
-    }
-    if (lane == 0) {
-      const float mean = ss / cnt;
-      const float var = fmaxf(qq / cnt - mean * mean, 0.f);
-      a.stats[static_cast<size_t>(n) * a.G + g] = make_float2(mean, rsqrtf(var + a.eps));
-    }
-  }
-  if (threadIdx.x == 0) a.counter[n] = 0;  // ready for the next launch
 }
 
-// phase 3: normalise + affine + optional SiLU, same tiling as phase 1.
-__global__ void __launch_bounds__(GN_THREADS) k5_gn_apply_kernel(const GnArgs a) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int pairs = a.C >> 1, cg2 = (a.C / a.G) >> 1;
-  const int p = blockIdx.x * 32 + lane;
-  const int slab = blockIdx.y, n = blockIdx.z;
-  const int r0 = slab * GN_ROWS;
-  const size_t base = static_cast<size_t>(n) * a.HW * pairs + p;
-  const uint32_t* xb = reinterpret_cast<const uint32_t*>(a.x) + base;
-  uint32_t* yb = reinterpret_cast<uint32_t*>(a.y) + base;
-  uint32_t v[GN_ROWS / GN_WARPS];
+__global__ void __launch_bounds__(512) k5_gn_vec_stats_kernel(const GnVecArgs a) {
+  extern __shared__ float2 s_pair[];  // [ty][C/2] pair sums
+  const int c8 = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int vec_per_row = a.C >> 3, pairs = a.C >> 1;
+  const int r0 = slab * a.rows_per_slab, r1 = min(a.HW, r0 + a.rows_per_slab);
+  const uint4* xb = reinterpret_cast<const uint4*>(a.x) + static_cast<size_t>(n) * a.HW * vec_per_row + c8;
+  float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.bias) unpack8(reinterpret_cast<const uint4*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[c8], b);
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  int r = r0 + ty;
+  for (; r + 3 * TY < r1; r += 4 * TY) {  // four rows in flight
+    uint4 v[4];
 #pragma unroll
-  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
-    const int r = r0 + warp + i * GN_WARPS;
-    v[i] = (r < a.HW) ? xb[static_cast<size_t>(r) * pairs] : 0u;
-  }
-  const float2 st = a.stats[static_cast<size_t>(n) * a.G + p / cg2];
-  const float2 gam = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.gamma)[p]);
-  const float2 bet = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.beta)[p]);
-  float2 b = make_float2(0.f, 0.f);
-  if (a.bias) b = bf2_to_f2(reinterpret_cast<const uint32_t*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[p]);
-  // y = (x + b - mean) * rstd * gamma + beta  =  x * sc + sh
-  const float scx = st.y * gam.x, scy = st.y * gam.y;
-  const float shx = (b.x - st.x) * scx + bet.x, shy = (b.y - st.x) * scy + bet.y;
+    for (int u = 0; u < 4; ++u) v[u] = xb[static_cast<size_t>(r + u * TY) * vec_per_row];
 #pragma unroll
-  for (int i = 0; i < GN_ROWS / GN_WARPS; ++i) {
-    const int r = r0 + warp + i * GN_WARPS;
-    if (r < a.HW) {
-      const float2 f = bf2_to_f2(v[i]);
-      float ox = f.x * scx + shx, oy = f.y * scy + shy;
-      if (a.act_silu) {
-        ox = ox / (1.0f + __expf(-ox));
-        oy = oy / (1.0f + __expf(-oy));
+    for (int u = 0; u < 4; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float x0 = f[2 * k] + b[2 * k], x1 = f[2 * k + 1] + b[2 * k + 1];
+        s[k] += x0 + x1;
+        q[k] += x0 * x0 + x1 * x1;
       }
-      __nv_bfloat162 o = __floats2bfloat162_rn(ox, oy);
-      yb[static_cast<size_t>(r) * pairs] = *reinterpret_cast<uint32_t*>(&o);
     }
   }
+  for (; r < r1; r += TY) {
+    float f[8];
+    unpack8(xb[static_cast<size_t>(r) * vec_per_row], f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x0 = f[2 * k] + b[2 * k], x1 = f[2 * k + 1] + b[2 * k + 1];
+      s[k] += x0 + x1;
+      q[k] += x0 * x0 + x1 * x1;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s_pair[ty * pairs + c8 * 4 + k] = make_float2(s[k], q[k]);
+  __syncthreads();
+  // group g <- its C/G/2 pairs over all ty, fixed order
+  const int tid = ty * blockDim.x + c8, cg2 = (a.C / a.G) >> 1;
+  if (tid < a.G) {
+    float ss = 0.f, qq = 0.f;
+    for (int t = 0; t < TY; ++t)
+      for (int k = 0; k < cg2; ++k) {
+        const float2 v = s_pair[t * pairs + tid * cg2 + k];
+        ss += v.x;
+        qq += v.y;
+      }
+    a.partial[(static_cast<size_t>(n) * GN_VEC_MAX_SLABS + slab) * a.G + tid] = make_float2(ss, qq);
+  }
+}
+
+__global__ void __launch_bounds__(32) k5_gn_vec_finalize_kernel(const GnVecArgs a) {
+  const int g = blockIdx.x, n = blockIdx.y, lane = threadIdx.x;
+  float ss = 0.f, qq = 0.f;
+  for (int sl = lane; sl < a.slabs; sl += 32) {
+    const float2 v = a.partial[(static_cast<size_t>(n) * GN_VEC_MAX_SLABS + sl) * a.G + g];
+    ss += v.x;
+    qq += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    qq += __shfl_xor_sync(0xffffffffu, qq, o);
+  }
+  if (lane == 0) {
+    const float cnt = static_cast<float>(a.HW) * (a.C / a.G);
+    const float mean = ss / cnt;
+    a.stats[static_cast<size_t>(n) * a.G + g] = make_float2(mean, rsqrtf(fmaxf(qq / cnt - mean * mean, 0.f) + a.eps));
+  }
+}
+
+__global__ void __launch_bounds__(512) k5_gn_vec_apply_kernel(const GnVecArgs a) {
+  const int c8 = threadIdx.x, ty = threadIdx.y, TY = blockDim.y;
+  const int n = blockIdx.y, slab = blockIdx.x;
+  const int vec_per_row = a.C >> 3, cg = a.C / a.G;
+  const int r0 = slab * a.rows_per_slab, r1 = min(a.HW, r0 + a.rows_per_slab);
+  const size_t base = static_cast<size_t>(n) * a.HW * vec_per_row + c8;
+  const uint4* xb = reinterpret_cast<const uint4*>(a.x) + base;
+  uint4* yb = reinterpret_cast<uint4*>(a.y) + base;
+  float sc[8], sh[8];
+  {
+    float gam[8], bet[8], b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unpack8(reinterpret_cast<const uint4*>(a.gamma)[c8], gam);
+    unpack8(reinterpret_cast<const uint4*>(a.beta)[c8], bet);
+    if (a.bias) unpack8(reinterpret_cast<const uint4*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[c8], b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float2 st = a.stats[static_cast<size_t>(n) * a.G + (c8 * 8 + k) / cg];
+      sc[k] = st.y * gam[k];
+      sh[k] = (b[k] - st.x) * sc[k] + bet[k];
+    }
+  }
+  auto emit = [&](const uint4& v, int row) {
+    float f[8];
+    unpack8(v, f);
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float y0 = f[2 * k] * sc[2 * k] + sh[2 * k], y1 = f[2 * k + 1] * sc[2 * k + 1] + sh[2 * k + 1];
+      if (a.act_silu) {
+        y0 = y0 / (1.0f + __expf(-y0));
+        y1 = y1 / (1.0f + __expf(-y1));
+      }
+      __nv_bfloat162 p = __floats2bfloat162_rn(y0, y1);
+      o[k] = *reinterpret_cast<uint32_t*>(&p);
+    }
+    yb[static_cast<size_t>(row) * vec_per_row] = make_uint4(o[0], o[1], o[2], o[3]);
+  };
+  int r = r0 + ty;
+  for (; r + 3 * TY < r1; r += 4 * TY) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = xb[static_cast<size_t>(r + u * TY) * vec_per_row];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) emit(v[u], r + u * TY);
+  }
+  for (; r < r1; r += TY) emit(xb[static_cast<size_t>(r) * vec_per_row], r);
 }
 
 // K5 fast path: one thread-block CLUSTER per (sample, group).  Each CTA of the cluster pulls its
@@ -413,13 +430,13 @@ __global__ void __launch_bounds__(256) k6_geglu_kernel(const __nv_bfloat16* __re
 
 }  // namespace
 
-static inline int64_t gn_counter_bytes(int N) { return ((static_cast<int64_t>(N) * 4 + 255) / 256) * 256; }
 }  // namespace fd
 
 extern "C" int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G) {
-  // [N ticket counters (must be zero-initialised once)] [partials] [stats]
-  const int64_t slabs = (HW + fd::GN_STAT_ROWS - 1) / fd::GN_STAT_ROWS;
-  return fd::gn_counter_bytes(N) + (static_cast<int64_t>(N) * slabs * (C / 2) + static_cast<int64_t>(N) * G) * 8;
+  // streaming path: per-slab per-group partials + per-group statistics (float2 each)
+  (void)HW;
+  (void)C;
+  return (static_cast<int64_t>(N) * fd::GN_VEC_MAX_SLABS * G + static_cast<int64_t>(N) * G) * 8;
 }
 
 extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
@@ -429,47 +446,40 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && workspace_dev && y_bf16_dev,
              "fd_groupnorm_act: NULL pointer");
   FD_REQUIRE(N > 0 && HW > 0 && C > 0, "fd_groupnorm_act: non-positive shape");
-  FD_REQUIRE(G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 2 == 0 && C % 64 == 0,
-             "fd_groupnorm_act: need G <= %d, C %% G == 0, even channels per group, C %% 64 == 0 (C=%d G=%d)",
+  FD_REQUIRE(G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 2 == 0 && C % 64 == 0 && C <= 4096,
+             "fd_groupnorm_act: need G <= %d, C %% G == 0, even channels per group, C %% 64 == 0, C <= 4096 (C=%d G=%d)",
              GN_MAX_GROUPS, C, G);
-  const int slabs = (HW + GN_ROWS - 1) / GN_ROWS;
-  FD_REQUIRE(N <= 65535 && slabs <= 65535, "fd_groupnorm_act: shape exceeds grid limits");
-  FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 8 == 0, "fd_groupnorm_act: workspace must be 8-byte aligned");
-  FD_REQUIRE(!bias_bf16_dev || (bias_row_stride >= C && bias_row_stride % 2 == 0 &&
-                                reinterpret_cast<uintptr_t>(bias_bf16_dev) % 4 == 0),
-             "fd_groupnorm_act: bias row stride must be even and >= C, pointer 4-byte aligned");
+  FD_REQUIRE(N <= 65535, "fd_groupnorm_act: N exceeds grid limits");
+  auto mis16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 != 0; };
+  FD_REQUIRE(!mis16(x_bf16_dev) && !mis16(y_bf16_dev) && !mis16(gamma_bf16_dev) && !mis16(beta_bf16_dev) &&
+                 reinterpret_cast<uintptr_t>(workspace_dev) % 8 == 0,
+             "fd_groupnorm_act: x / y / gamma / beta must be 16-byte aligned, workspace 8-byte aligned");
+  FD_REQUIRE(!bias_bf16_dev || (bias_row_stride >= C && bias_row_stride % 8 == 0 && !mis16(bias_bf16_dev)),
+             "fd_groupnorm_act: bias row stride must be a multiple of 8 and >= C, pointer 16-byte aligned");
   int rc = check_device();
   if (rc != FD_OK) return rc;
-  GnArgs a;
-  a.x = static_cast<const __nv_bfloat16*>(x_bf16_dev);
-  a.bias = static_cast<const __nv_bfloat16*>(bias_bf16_dev);
-  a.bias_stride = bias_row_stride;
-  a.gamma = static_cast<const __nv_bfloat16*>(gamma_bf16_dev);
-  a.beta = static_cast<const __nv_bfloat16*>(beta_bf16_dev);
-  const int stat_slabs = (HW + GN_STAT_ROWS - 1) / GN_STAT_ROWS;
-  a.counter = static_cast<int*>(workspace_dev);
-  a.partial = reinterpret_cast<float2*>(static_cast<char*>(workspace_dev) + gn_counter_bytes(N));
-  a.stats = a.partial + static_cast<size_t>(N) * stat_slabs * (C / 2);
-  a.stat_slabs = stat_slabs;
-  a.y = static_cast<__nv_bfloat16*>(y_bf16_dev);
-  a.HW = HW;
-  a.C = C;
-  a.G = G;
-  a.slabs = slabs;
-  a.eps = eps;
-  a.act_silu = act_silu;
+  const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x_bf16_dev);
+  const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(bias_bf16_dev);
+  const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(gamma_bf16_dev);
+  const __nv_bfloat16* tp = static_cast<const __nv_bfloat16*>(beta_bf16_dev);
+  __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y_bf16_dev);
+  const int64_t total_bytes = static_cast<int64_t>(N) * HW * C * 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  {
-    // fast path: the whole group fits the shared memory of a cluster of <= 8 CTAs
+  static const int64_t cluster_max = [] {  // development override of the path switch
+    const char* e = getenv("FD_GN_CLUSTER_MAX_BYTES");
+    return e ? static_cast<int64_t>(atoll(e)) : GN_CLUSTER_MAX_BYTES;
+  }();
+  if (total_bytes <= cluster_max) {
+    // small, latency-bound activations: the whole group fits the shared memory of a cluster of <= 8 CTAs
     const int64_t group_bytes = static_cast<int64_t>(HW) * (C / G) * 2;
     int cl = 1;
     while (cl < 8 && (group_bytes / cl > 48 * 1024 || static_cast<int64_t>(N) * G * cl < 2 * sm_count())) cl *= 2;
     while (cl > 1 && HW < cl * 8) cl /= 2;
     const int rows_per_cta = (HW + cl - 1) / cl;
     const int64_t smem = static_cast<int64_t>(rows_per_cta) * (C / G) * 2;
-    if (smem <= 96 * 1024 && C / G <= 2 * GN_MAX_CG2 && static_cast<int64_t>(N) * G * cl <= 0x7fffffff) {
+    if (smem <= 96 * 1024 && C / G <= 2 * GN_MAX_CG2) {
       GnClusterArgs c;
-      c.x = a.x; c.bias = a.bias; c.bias_stride = a.bias_stride; c.gamma = a.gamma; c.beta = a.beta; c.y = a.y;
+      c.x = xp; c.bias = bp; c.bias_stride = bias_row_stride; c.gamma = gp; c.beta = tp; c.y = yp;
       c.HW = HW; c.C = C; c.G = G; c.rows_per_cta = rows_per_cta; c.eps = eps; c.act_silu = act_silu;
       static thread_local int attr_device = -1;
       int dev = 0;
@@ -494,9 +504,27 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
       return FD_OK;
     }
   }
-  dim3 grid(C / 64, slabs, N);
-  k5_gn_stats_kernel<<<dim3(C / 64, stat_slabs, N), GN_THREADS, 0, st>>>(a);
-  k5_gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(a);
+  // streaming path
+  GnVecArgs v;
+  v.x = xp; v.bias = bp; v.bias_stride = bias_row_stride; v.gamma = gp; v.beta = tp; v.y = yp;
+  v.HW = HW; v.C = C; v.G = G; v.eps = eps; v.act_silu = act_silu;
+  const int tx = C / 8;
+  int ty = 256 / tx;
+  if (ty < 1) ty = 1;
+  // ~64 KB of input per CTA, at most GN_VEC_MAX_SLABS slabs per sample
+  int rows = (64 * 1024) / (C * 2);
+  if (rows < 4 * ty) rows = 4 * ty;
+  int slabs = (HW + rows - 1) / rows;
+  if (slabs > GN_VEC_MAX_SLABS) slabs = GN_VEC_MAX_SLABS;
+  v.rows_per_slab = (HW + slabs - 1) / slabs;
+  v.slabs = (HW + v.rows_per_slab - 1) / v.rows_per_slab;
+  v.partial = static_cast<float2*>(workspace_dev);
+  v.stats = v.partial + static_cast<size_t>(N) * GN_VEC_MAX_SLABS * G;
+  dim3 grid(v.slabs, N), block(tx, ty);
+  const size_t smem = static_cast<size_t>(ty) * (C / 2) * sizeof(float2);
+  k5_gn_vec_stats_kernel<<<grid, block, smem, st>>>(v);
+  k5_gn_vec_finalize_kernel<<<dim3(G, N), 32, 0, st>>>(v);
+  k5_gn_vec_apply_kernel<<<grid, block, 0, st>>>(v);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }
