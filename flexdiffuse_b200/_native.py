@@ -342,7 +342,7 @@ def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                                 ptr(y), N, H * W, Cc, groups, float(eps),
                                 int(silu), bias_stride, stream_ptr(x.device))
     check(rc, 'fd_groupnorm_act')
-    count_launch(1 if x.numel() * 2 <= (12 << 20) else 3)  # cluster kernel or stats/finalize/apply
+    count_launch(1 if x.numel() * 2 <= (8 << 20) else 3)  # cluster kernel or stats/finalize/apply
     return y
 
 

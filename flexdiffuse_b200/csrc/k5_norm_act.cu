@@ -28,7 +28,7 @@ constexpr int GN_THREADS = 256;   // 8 warps: warp w takes rows w, w+8, ... of t
 constexpr int GN_WARPS = GN_THREADS / 32;
 constexpr int GN_MAX_GROUPS = 32;
 constexpr int GN_VEC_MAX_SLABS = 512;               // streaming path: slabs per sample
-constexpr int64_t GN_CLUSTER_MAX_BYTES = 12 << 20;  // larger activations take the streaming path
+constexpr int64_t GN_CLUSTER_MAX_BYTES = 8 << 20;   // larger activations take the streaming path
 constexpr int GN_MAX_CG2 = 64;     // channel pairs per group on the cluster path (C/G <= 128)
 
 __device__ __forceinline__ float2 bf2_to_f2(uint32_t v) {
