@@ -22,6 +22,8 @@ class Enc:
         self.dev, self.cache = dev, {}
 
     def prompt(self, p):
+        if isinstance(p, (list, tuple)):  # encode_schema batches every prompt into one call
+            return torch.cat([self.prompt(q) for q in p])
         if p not in self.cache:
             g = torch.Generator(device=self.dev).manual_seed(len(self.cache) + 3)
             self.cache[p] = torch.randn(1, 77, 768, device=self.dev, generator=g)
