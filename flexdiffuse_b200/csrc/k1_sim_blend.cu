@@ -539,6 +539,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
               const int orr = __shfl_xor_sync(0xffffffffu, r_best, o);
               argmax_combine(s, r_best, os, orr);
             }
+            __syncwarp();  // every lane has finished reading assigned[] / col_*[] before lane 0 updates them
             if (r_best >= 0 && s > 0.f) {
               if (lane == 0) {
                 const int i = sm.col_i[r_best];
@@ -576,6 +577,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
             float s;
             int i;
             warp_col_argmax(pt + r * PT_STRIDE, A, sm.used, lane, s, i);
+            __syncwarp();  // all lanes are past their col_i[r] test before lane 0 rewrites it
             if (lane == 0) {
               sm.col_s[r] = s;
               sm.col_i[r] = i;
