@@ -265,6 +265,29 @@ def kernel_rooflines(dev, unet, peaks):
     return out
 
 
+def guide_embeds_e2e(dev, n=5):
+    '''`Guide.embeds(prompt, image)` end to end on the GPU (BASELINE.json configs[0] on the B200):
+    random-init CLIP ViT-L/14 towers in PyTorch + K1, one prompt x one 512x512 guide image.
+    Returns calls per second (the survey measured 0.67 s per call for the reference on 8 CPU cores).'''
+    import numpy as np
+    from PIL import Image
+    from flexdiffuse_b200 import factory
+    from flexdiffuse_b200.guidance import Guide
+    clip = factory.build_clip(dev)
+    guide = Guide(clip, factory.FakeTokenizer(), device=str(dev))
+    img = Image.fromarray((np.random.RandomState(0).rand(512, 512, 3) * 255).astype('uint8'))
+    with torch.no_grad():
+        for _ in range(2):
+            out = guide.embeds('a photograph of an astronaut riding a horse', img, guide_clustered=0.0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            out = guide.embeds('a photograph of an astronaut riding a horse', img, guide_clustered=0.0)
+        torch.cuda.synchronize()
+    assert tuple(out.shape) == (1, 77, 768)
+    return n / (time.perf_counter() - t0)
+
+
 # ------------------------------------------------------------------ main arm
 class _Enc:
     '''Stand-in for CLIPEncoder on the text-only workload: the CLIP towers stay in PyTorch
@@ -434,6 +457,7 @@ def main():
         line['cpu_baseline'] = base
         cb = cpu_blend_baseline()
         line['blends'] = {'gpu_blends_per_s': kr['k1']['blends_per_s'],
+                          'gpu_guide_embeds_calls_per_s': guide_embeds_e2e(dev),
                           'cpu_blends_per_s': cb, 'cpu_kind': 'port',
                           'cpu_cores': os.cpu_count(),
                           'workload': '1 prompt [77,768] x 1 guide image [257,768], defaults '
