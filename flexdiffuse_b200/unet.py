@@ -138,12 +138,22 @@ class SelfAttention(nn.Module):
         self.to_v = nn.Linear(dim, dim, bias=False)
         self.to_out = nn.Linear(dim, dim)
 
+    def _qkv_weight(self) -> torch.Tensor:
+        '''to_q | to_k | to_v stacked into one [3C, C] matrix (one GEMM instead of three), cached
+        until any of the three parameters changes.'''
+        ws = (self.to_q.weight, self.to_k.weight, self.to_v.weight)
+        key = tuple((w.data_ptr(), w._version) for w in ws)
+        cached = self.__dict__.get('_qkv_cache')
+        if cached is None or cached[0] != key:
+            cached = (key, torch.cat([w.detach() for w in ws]).contiguous())
+            self.__dict__['_qkv_cache'] = cached
+        return cached[1]
+
     def forward(self, x):
         B, N, C = x.shape
         h = self.heads
-        q = self.to_q(x).view(B, N, h, C // h).transpose(1, 2)
-        k = self.to_k(x).view(B, N, h, C // h).transpose(1, 2)
-        v = self.to_v(x).view(B, N, h, C // h).transpose(1, 2)
+        qkv = F.linear(x, self._qkv_weight()).view(B, N, 3, h, C // h)
+        q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         o = F.scaled_dot_product_attention(q, k, v)
         return self.to_out(o.transpose(1, 2).reshape(B, N, C))
 
