@@ -158,6 +158,13 @@ def cpu_blend_baseline(n: int = 8):
     return n / (time.perf_counter() - t0)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu` captures of exactly these
+# microbenchmark launches (profiles/r01/k3_dram_traffic_16sites.csv: 195.4 MB over the 16 K3 launches;
+# profiles/r01/kernels_full_raw_subset_final.csv for K4 / K2 / K1).  Output writes that are still
+# resident in the 126 MB L2 when a kernel ends are not counted by the DRAM counters.
+NCU_TRAFFIC_BYTES = {'k3': 12.21e6, 'k4': 237.6e6, 'k2': 41.8e6, 'k1': 443.2e6}
+
+
 # ------------------------------------------------------------------ kernel microbenches
 def _time_cuda(fn, iters, flush=None):
     st = torch.cuda.current_stream()
@@ -212,7 +219,8 @@ def kernel_rooflines(dev, unet, peaks):
         run_k3()
     t = _time_cuda(g3.replay, 10, flush)
     out['k3'] = dict(bound='hbm', achieved=alg_bytes / t / 1e9, peak=peaks['hbm'],
-                     unit='GB/s', frac=alg_bytes / t / 1e9 / peaks['hbm'], traffic=None,
+                     unit='GB/s', frac=alg_bytes / t / 1e9 / peaks['hbm'],
+                     traffic=NCU_TRAFFIC_BYTES['k3'], algorithmic_bytes_per_launch=alg_bytes / 16,
                      kernel='k3_cross_attn_kernel (16 attn2 sites, 8 samples)',
                      launches=16, avg_launch_us=t / 16 * 1e6,
                      tflops=alg_flops / t / 1e12, peak_of=peaks['source'])
@@ -228,7 +236,8 @@ def kernel_rooflines(dev, unet, peaks):
     f4()
     t = _time_cuda(f4, 20)
     out['k4'] = dict(bound='hbm', achieved=16 * n / t / 1e9, peak=peaks['hbm'], unit='GB/s',
-                     frac=16 * n / t / 1e9 / peaks['hbm'], traffic=None,
+                     frac=16 * n / t / 1e9 / peaks['hbm'], traffic=NCU_TRAFFIC_BYTES['k4'],
+                     algorithmic_bytes_per_launch=16 * n,
                      kernel='k4_cfg_sched_kernel (DDIM, fp32, 1024 samples)',
                      avg_launch_us=t * 1e6, peak_of=peaks['source'])
     del u, c, x, xo
@@ -241,7 +250,7 @@ def kernel_rooflines(dev, unet, peaks):
     t = _time_cuda(f2, 10, flush)
     fl = 2 * 9 * 80 * 768 * 24960
     out['k2'] = dict(bound='tensor', achieved=fl / t / 1e12, peak=peaks['tensor'],
-                     unit='TFLOP/s', frac=fl / t / 1e12 / peaks['tensor'], traffic=None,
+                     unit='TFLOP/s', frac=fl / t / 1e12 / peaks['tensor'], traffic=NCU_TRAFFIC_BYTES['k2'],
                      kernel='k2_gemm_kernel (M=720,N=24960,K=768; 9 contexts)',
                      avg_launch_us=t * 1e6, peak_of=peaks['source'])
     # ---- K1: blends/s -- 1024 prompts x 1 shared guide image, default parameters
@@ -258,7 +267,8 @@ def kernel_rooflines(dev, unet, peaks):
     fl = 3 * 2 * 384 * 80 * 768 * nb   # 3-pass tf32, padded tiles
     by = nb * (2 * 77 * 768 * 4) + 257 * 768 * 4
     out['k1'] = dict(bound='hbm', achieved=by / t / 1e9, peak=peaks['hbm'], unit='GB/s',
-                     frac=by / t / 1e9 / peaks['hbm'], traffic=None,
+                     frac=by / t / 1e9 / peaks['hbm'], traffic=NCU_TRAFFIC_BYTES['k1'],
+                     algorithmic_bytes_per_launch=by,
                      kernel='k1_sim_blend_kernel (1024 prompts x 1 guide)',
                      blends_per_s=nb / t, issued_tf32_tflops=fl / t / 1e12,
                      avg_launch_us=t * 1e6, peak_of=peaks['source'])
