@@ -12,7 +12,8 @@
 //   warp 1     : single-thread tcgen05.mma issuer (M128 N256 K16), accumulator in TMEM
 //   warps 2-5  : epilogue (tcgen05.ld -> bf16 -> global)
 // The accumulator is double-buffered (2 x 256 TMEM columns), so the epilogue of tile i runs under
-// the mainloop of tile i+1.  v1 (one 128x128 tile per CTA, no overlap) was bound by L2->SM operand
+// the mainloop of tile i+1.  v3: when the number of m tiles is even the kernel runs as 2-CTA clusters
+// whose CTAs share one weight tile through TMA multicast (see PAIR below).  v1 (one 128x128 tile per CTA, no overlap) was bound by L2->SM operand
 // traffic at 64 FLOP/B per tile (profiles/r01/SUMMARY.md); 128x256 tiles need 25 % fewer bytes.
 #include "fd_common.cuh"
 
@@ -30,6 +31,12 @@ constexpr int K2_THREADS = 192;
 constexpr int K2_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*bars*/;
 constexpr int TMEM_COLS = 2 * BN;
 
+// PAIR: launched as 2-CTA clusters; the two CTAs of a pair work on tiles (2q, 2q+1) = the same
+// weight (B) tile and adjacent m tiles.  Each CTA TMA-loads its own A tile and HALF of the B tile,
+// multicast into both CTAs' shared memory, which halves the L2 -> SM traffic of the dominant
+// operand.  A stage may only be refilled once BOTH CTAs' MMAs have consumed it, so the MMA warps
+// commit to the empty barrier of both CTAs (count 2).
+template <bool PAIR>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                __nv_bfloat16* __restrict__ out, int M, int N, int K, int m_tiles, int n_tiles) {
@@ -46,13 +53,17 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int num_kb = K / BK;
   const int total_tiles = m_tiles * n_tiles;
+  const uint32_t crank = PAIR ? cluster_cta_rank() : 0;
+  // tile walk: single CTAs stride over tiles; pairs stride over tile pairs
+  const int first_tile = PAIR ? 2 * static_cast<int>(blockIdx.x >> 1) + static_cast<int>(crank) : static_cast<int>(blockIdx.x);
+  const int tile_stride = PAIR ? 2 * static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], PAIR ? 2 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
@@ -66,20 +77,27 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_barrier();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (elect_one()) {
       int it = 0;  // running k-block counter across tiles: stage = it % STAGES
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
         const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait_backoff(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           tma_load_2d(smem + s * STAGE_BYTES, &tm_a, &full_bar[s], kb * BK, m_blk * BM);
-          tma_load_2d(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tm_b, &full_bar[s], kb * BK, n_blk * BN);
+          if (PAIR) {
+            // my half of the weight tile (128 of its 256 rows), delivered to both CTAs
+            tma_load_2d_mcast(smem + s * STAGE_BYTES + A_STAGE_BYTES + crank * (B_STAGE_BYTES / 2), &tm_b,
+                              &full_bar[s], kb * BK, n_blk * BN + static_cast<int>(crank) * (BN / 2), 0x3);
+          } else {
+            tma_load_2d(smem + s * STAGE_BYTES + A_STAGE_BYTES, &tm_b, &full_bar[s], kb * BK, n_blk * BN);
+          }
         }
       }
     }
@@ -87,7 +105,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(UMMA_BF16, BM, BN, 0, 0);
       int it = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
         const int acc = local & 1;
         mbar_wait_backoff(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
@@ -101,7 +119,8 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // 16 bf16 = 32 B along K inside the swizzle row: +2
             mma_f16_ss(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          tc_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+          if (PAIR) tc_commit_mcast(&empty_bar[s], 0x3);  // both producers write into this stage
+          else tc_commit(&empty_bar[s]);                  // smem slot reusable once these MMAs retire
         }
         tc_commit(&tmem_full[acc]);  // accumulator complete
       }
@@ -111,7 +130,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
       const int acc = local & 1;
       mbar_wait(&tmem_full[acc], (local >> 1) & 1);
@@ -149,6 +168,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_barrier();  // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -193,15 +213,43 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
   int dev = 0;
   FD_CUDA_OK(cudaGetDevice(&dev));
   if (attr_device != dev) {
-    FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
+    FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
+    FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM));
     attr_device = dev;
   }
   const int sms = sm_count();
   if (sms <= 0) return set_error(FD_ERR_CUDA, "fd_kv_project: cannot query SM count");
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
-  k2_gemm_kernel<<<total < sms ? total : sms, K2_THREADS, K2_SMEM, static_cast<cudaStream_t>(stream)>>>(
-      tm_a, tm_b, static_cast<__nv_bfloat16*>(out_bf16_dev), M, N, K, m_tiles, n_tiles);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(out_bf16_dev);
+  if (m_tiles % 2 == 0 && sms >= 2) {
+    // paired path: tiles 2q and 2q+1 share their weight tile (m is the fast index and m_tiles is even)
+    CUtensorMap tm_bh;  // half-height box of the weight tile: each CTA of a pair loads 128 of the 256 rows
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BK, BN / 2};
+    rc = encode_tmap(&tm_bh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_bf16_dev, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+    int pairs = total / 2, max_pairs = sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * (pairs < max_pairs ? pairs : max_pairs)));
+    cfg.blockDim = dim3(K2_THREADS);
+    cfg.dynamicSmemBytes = K2_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k2_gemm_kernel<true>, tm_a, tm_bh, outp, M, N, K, m_tiles, n_tiles));
+    return FD_OK;
+  }
+  k2_gemm_kernel<false><<<total < sms ? total : sms, K2_THREADS, K2_SMEM, st>>>(tm_a, tm_b, outp, M, N, K, m_tiles,
+                                                                               n_tiles);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }
