@@ -10,7 +10,7 @@
 // (m fastest, so the CTAs running together share one weight tile in L2):
 //   warp 0     : TMA producer, 4-stage mbarrier ring of {A 128x64, B 256x64} SWIZZLE_128B tiles
 //   warp 1     : single-thread tcgen05.mma issuer (M128 N256 K16), accumulator in TMEM
-//   warps 2-5  : epilogue (tcgen05.ld -> bf16 -> global)
+//   warps 2-5  : epilogue (tcgen05.ld -> bf16 -> swizzled smem staging -> TMA store)
 // The accumulator is double-buffered (2 x 256 TMEM columns), so the epilogue of tile i runs under
 // the mainloop of tile i+1.  v3: when the number of m tiles is even the kernel runs as 2-CTA clusters
 // whose CTAs share one weight tile through TMA multicast (see PAIR below).  v1 (one 128x128 tile per CTA, no overlap) was bound by L2->SM operand
@@ -28,7 +28,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int B_STAGE_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
 constexpr int K2_THREADS = 192;
-constexpr int K2_SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*bars*/;
+constexpr int OUT_CHUNK_BYTES = BM * 64 * 2;  // epilogue staging: 128 rows x 64 bf16, SWIZZLE_128B, two buffers
+constexpr int K2_SMEM = STAGES * STAGE_BYTES + 2 * OUT_CHUNK_BYTES + 1024 /*align*/ + 256 /*bars*/;
 constexpr int TMEM_COLS = 2 * BN;
 
 // PAIR: launched as 2-CTA clusters; the two CTAs of a pair work on tiles (2q, 2q+1) = the same
@@ -39,11 +40,12 @@ constexpr int TMEM_COLS = 2 * BN;
 template <bool PAIR>
 __global__ void __launch_bounds__(K2_THREADS, 1)
 k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-               __nv_bfloat16* __restrict__ out, int M, int N, int K, int m_tiles, int n_tiles) {
+               const __grid_constant__ CUtensorMap tm_out, int M, int N, int K, int m_tiles, int n_tiles) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;  // 2 x OUT_CHUNK_BYTES
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + 2 * OUT_CHUNK_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -61,6 +63,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tm_a);
     tma_prefetch_desc(&tm_b);
+    tma_prefetch_desc(&tm_out);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], PAIR ? 2 : 1);
@@ -88,7 +91,7 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait_backoff(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full_bar[s], STAGE_BYTES);
           tma_load_2d(smem + s * STAGE_BYTES, &tm_a, &full_bar[s], kb * BK, m_blk * BM);
           if (PAIR) {
@@ -107,12 +110,12 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       int it = 0, local = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
         const int acc = local & 1;
-        mbar_wait_backoff(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this buffer
+        mbar_wait(&tmem_empty[acc], ((local >> 1) & 1) ^ 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t d = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait_backoff(&full_bar[s], (it / STAGES) & 1);
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES), 16, 1024);
           const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE_BYTES + A_STAGE_BYTES), 16, 1024);
@@ -126,45 +129,55 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       }
     }
   } else {
-    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32)
+    // epilogue: warp w may only touch TMEM lanes [32*(w%4), +32).  Rows go to a SWIZZLE_128B staging
+    // tile in shared memory and leave through TMA stores (full 128-byte lines, clipped at the
+    // matrix edges) -- a thread-per-row store pattern writes half-filled 32-byte sectors.
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    int local = 0;
+    const bool issuer = threadIdx.x == 64;  // first epilogue thread issues the TMA stores
+    int local = 0, chunk_no = 0;
     for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
       const int m_blk = tile % m_tiles, n_blk = tile / m_tiles;
       const int acc = local & 1;
       mbar_wait(&tmem_full[acc], (local >> 1) & 1);
       tc_fence_after();
-      const int64_t g_row = static_cast<int64_t>(m_blk) * BM + row;
-      const int n0 = n_blk * BN;
       const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 64) {
+      for (int c0 = 0; c0 < BN; c0 += 64, ++chunk_no) {
         uint32_t v[4][16];
 #pragma unroll
         for (int g = 0; g < 4; ++g) tmem_ld_x16(tbase + c0 + 16 * g, v[g]);
         tmem_ld_wait();
-        if (g_row < M) {
+        uint8_t* buf = out_stage + (chunk_no & 1) * OUT_CHUNK_BYTES;
+        // the store that last read this buffer (two chunks ago) must have finished reading it
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int c = c0 + 16 * g;
-            uint32_t pk[8];
+        for (int g = 0; g < 4; ++g) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              __nv_bfloat162 b =
-                  __floats2bfloat162_rn(__uint_as_float(v[g][2 * j]), __uint_as_float(v[g][2 * j + 1]));
+          for (int h = 0; h < 2; ++h) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[g][8 * h + 2 * j]),
+                                                       __uint_as_float(v[g][8 * h + 2 * j + 1]));
               pk[j] = *reinterpret_cast<uint32_t*>(&b);
             }
-            __nv_bfloat16* dst = out + g_row * N + n0 + c;
-            if (n0 + c + 8 <= N) *reinterpret_cast<uint4*>(dst) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            if (n0 + c + 16 <= N) *reinterpret_cast<uint4*>(dst + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            *reinterpret_cast<uint4*>(buf + sw128_offset(row, 2 * g + h)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (issuer) {
+          tma_store_2d(&tm_out, buf, n_blk * BN + c0, m_blk * BM);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (issuer) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -209,6 +222,15 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
+  CUtensorMap tm_out;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(M)};
+    uint64_t strides[1] = {static_cast<uint64_t>(N) * 2};
+    uint32_t box[2] = {64, BM};
+    rc = encode_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_bf16_dev, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+  }
   static thread_local int attr_device = -1;
   int dev = 0;
   FD_CUDA_OK(cudaGetDevice(&dev));
@@ -222,7 +244,6 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(out_bf16_dev);
   if (m_tiles % 2 == 0 && sms >= 2) {
     // paired path: tiles 2q and 2q+1 share their weight tile (m is the fast index and m_tiles is even)
     CUtensorMap tm_bh;  // half-height box of the weight tile: each CTA of a pair loads 128 of the 256 rows
@@ -245,10 +266,10 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k2_gemm_kernel<true>, tm_a, tm_bh, outp, M, N, K, m_tiles, n_tiles));
+    FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k2_gemm_kernel<true>, tm_a, tm_bh, tm_out, M, N, K, m_tiles, n_tiles));
     return FD_OK;
   }
-  k2_gemm_kernel<false><<<total < sms ? total : sms, K2_THREADS, K2_SMEM, st>>>(tm_a, tm_b, outp, M, N, K, m_tiles,
+  k2_gemm_kernel<false><<<total < sms ? total : sms, K2_THREADS, K2_SMEM, st>>>(tm_a, tm_b, tm_out, M, N, K, m_tiles,
                                                                                n_tiles);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
