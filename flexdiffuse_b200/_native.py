@@ -15,7 +15,7 @@ import torch
 LIB_NAME = 'libflexdiffuse_b200.so'
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
 
-FD_ABI_VERSION = 1
+FD_ABI_VERSION = 2
 FD_DTYPE_F32 = 0
 FD_DTYPE_BF16 = 1
 FD_BLEND_OK = 0
@@ -53,7 +53,12 @@ class TweenParams(C.Structure):
     _fields_ = [('threshold_floor', C.c_double), ('threshold_mult', C.c_double),
                 ('clustered', C.c_double), ('max_guidance', C.c_double),
                 ('header_max', C.c_double), ('align_mode', C.c_int),
-                ('mapping_reuse', C.c_int)]
+                ('mapping_reuse', C.c_int), ('blend_mode', C.c_int),
+                ('reserved', C.c_int)]
+
+
+BLEND_MODE_LERP = 0
+BLEND_MODE_SLERP = 1
 
 
 _lib: Optional[C.CDLL] = None

@@ -90,6 +90,7 @@ struct K1Smem {
   unsigned int used[MAX_TILES * 128 / 32];  // bitmask of guide tokens already consumed
   float iw[MAXT + 16];
   int sel[MAXT + 16];
+  float slerp_a[MAXT + 16], slerp_b[MAXT + 16];  // FD_BLEND_MODE_SLERP row coefficients
   float rem[MAX_REM][NPAD];  // raw dot products of the remainder guide rows
   int pick_r, pick_i, flag;
   uint64_t full_bar[2], empty_bar[2], done_bar;
@@ -743,6 +744,41 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     }
     __syncthreads();
 
+    if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
+      // ---------------- 4b. slerp coefficients of the rows the reference would lerp: one warp per
+      // row reduces <base,alt>, |base|^2, |alt|^2 in a fixed order, lane 0 turns them into
+      // sin((1-w)O)/sin O and sin(wO)/sin O.  Nearly parallel rows keep the lerp expression.
+      for (int r = warp; r < T; r += K1_THREADS / 32) {
+        if (sm.sel[r] != 2) continue;
+        const float4* bp4 = reinterpret_cast<const float4*>(text + static_cast<size_t>(r) * D);
+        const float4* ap4 = reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[r]) * D);
+        float dot = 0.f, nb = 0.f, na = 0.f;
+        for (int c = lane; c < D / 4; c += 32) {
+          const float4 bv = __ldg(bp4 + c), av = __ldg(ap4 + c);
+          dot = fmaf(bv.x, av.x, fmaf(bv.y, av.y, fmaf(bv.z, av.z, fmaf(bv.w, av.w, dot))));
+          nb = fmaf(bv.x, bv.x, fmaf(bv.y, bv.y, fmaf(bv.z, bv.z, fmaf(bv.w, bv.w, nb))));
+          na = fmaf(av.x, av.x, fmaf(av.y, av.y, fmaf(av.z, av.z, fmaf(av.w, av.w, na))));
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          nb += __shfl_xor_sync(0xffffffffu, nb, o);
+          na += __shfl_xor_sync(0xffffffffu, na, o);
+        }
+        if (lane == 0) {
+          const float den = sqrtf(nb) * sqrtf(na);
+          const float cosv = den > 0.f ? dot / den : 1.0f;
+          if (fabsf(cosv) <= FD_SLERP_DOT_THRESHOLD) {
+            const float w = sm.iw[r];
+            const float theta = acosf(cosv), st = sinf(theta), tw = theta * w;
+            sm.slerp_a[r] = sinf(theta - tw) / st;
+            sm.slerp_b[r] = sinf(tw) / st;
+            sm.sel[r] = 3;
+          }
+        }
+      }
+      __syncthreads();
+    }
+
     if (p == p_begin) K1_STAMP(4);
     // ---------------- 5. select / lerp, 2 rows of 192 float4 per pass
     {
@@ -757,6 +793,12 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           const float4 av = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[r]) * D) + c);
           if (sel == 1) {
             o = av;
+          } else if (sel == 3) {
+            const float ca = sm.slerp_a[r], cb = sm.slerp_b[r];
+            o.x = __fadd_rn(__fmul_rn(ca, bv.x), __fmul_rn(cb, av.x));
+            o.y = __fadd_rn(__fmul_rn(ca, bv.y), __fmul_rn(cb, av.y));
+            o.z = __fadd_rn(__fmul_rn(ca, bv.z), __fmul_rn(cb, av.z));
+            o.w = __fadd_rn(__fmul_rn(ca, bv.w), __fmul_rn(cb, av.w));
           } else {
             const float w = sm.iw[r];
             // base + (alt - base) * iw, every op rounded separately like the torch expression

@@ -39,7 +39,7 @@ VERBOSE = False
 
 
 def _native_params(threshold_floor, threshold_mult, clustered, max_guidance,
-                   header_max, align_mode, mapping_reuse):
+                   header_max, align_mode, mapping_reuse, slerp=False):
     p = _native.TweenParams()
     p.threshold_floor = float(threshold_floor)
     p.threshold_mult = float(threshold_mult)
@@ -48,6 +48,8 @@ def _native_params(threshold_floor, threshold_mult, clustered, max_guidance,
     p.header_max = float(header_max)
     p.align_mode = int(align_mode)
     p.mapping_reuse = int(bool(mapping_reuse))
+    p.blend_mode = (_native.BLEND_MODE_SLERP if slerp
+                    else _native.BLEND_MODE_LERP)
     return p
 
 
@@ -87,7 +89,12 @@ class Tweener():
                  max_guidance: float = 0.5,
                  header_max: float = 0.15,
                  align_mode: int = GUIDE_ORDER_ALIGN,
-                 mapping_reuse: bool = True) -> None:
+                 mapping_reuse: bool = True,
+                 slerp: bool = False) -> None:
+        # `slerp` is the one argument the reference's Tweener (guidance.py:203-213) does
+        # not have: rows it would lerp are spherically interpolated instead (off by
+        # default, so the default object behaves exactly like the reference's)
+        self.slerp = slerp
         self.threshold_floor = threshold[0]
         self.threshold_mult = threshold[1]
         self.linear_start = linear[0]
@@ -102,7 +109,7 @@ class Tweener():
         return _native_params(self.threshold_floor, self.threshold_mult,
                               self.clustered, self.max_guidance,
                               self.header_max, self.align_mode,
-                              self.mapping_reuse)
+                              self.mapping_reuse, self.slerp)
 
     def _linear(self, steps: int, device) -> torch.Tensor:
         # guidance.py:231-233 -- torch.linspace on the host, exactly as the reference
@@ -203,8 +210,10 @@ class Guide():
                guide_max_guidance: float = 0.5,
                guide_header_max: float = 0.15,
                guide_mode: int = GUIDE_ORDER_ALIGN,
-               guide_reuse: bool = True) -> torch.Tensor:
-        '''Same arguments, defaults and return value as guidance.py:337-474.'''
+               guide_reuse: bool = True,
+               guide_slerp: bool = False) -> torch.Tensor:
+        '''Same arguments, defaults and return value as guidance.py:337-474
+        (`guide_slerp` is an extension, see Tweener).'''
         if isinstance(prompt, str):
             prompt = prompt.strip()
         elif isinstance(prompt, list):
@@ -231,7 +240,8 @@ class Guide():
                         guide_embeddings, self.encoder.prompt(mapping_concepts))
         tweener = Tweener((guide_threshold_floor, guide_threshold_mult),
                           guide_linear, guide_clustered, guide_max_guidance,
-                          guide_header_max, guide_mode, guide_reuse)
+                          guide_header_max, guide_mode, guide_reuse,
+                          guide_slerp)
 
         if text_embeddings is not None:
             if guide_embeddings is None:

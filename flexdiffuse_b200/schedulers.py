@@ -368,3 +368,24 @@ class LMSDiscreteScheduler(_SchedulerBase):
         sig = self.sigmas[t].to(original_samples.device)
         shape = (-1,) + (1,) * (original_samples.dim() - 1)
         return original_samples + noise * sig.view(shape)
+
+
+class EulerDiscreteScheduler(LMSDiscreteScheduler):
+    '''Euler update in sigma space: x' = x + (sigma[i+1] - sigma[i]) * eps.  EXTENSION -- the
+    reference pins diffusers 0.3.0, which has no Euler class; BASELINE.json's north_star names
+    one, and it is exactly the order-1 case of the LMS scheduler the reference drives at
+    /root/reference/pipeline/flex.py:271-284 (same sigma grid, same input scaling, same
+    step-index convention), so it is checked against LMSDiscreteScheduler(order=1): one K4
+    launch per step, no derivative history, the coefficient in closed form.'''
+    def lms_coefficient(self, order: int, t: int, current_order: int) -> float:
+        assert order == 1 and current_order == 0
+        sig = self.sigmas.numpy().astype(np.float64)
+        return float(sig[t + 1] - sig[t])
+
+    def fused_step(self, eps_uncond, eps_cond, guidance, use_cfg, timestep,
+                   sample, order: int = 1, out=None, scaled_out=None, **_):
+        return super().fused_step(eps_uncond, eps_cond, guidance, use_cfg,
+                                  timestep, sample, 1, out, scaled_out)
+
+    def step(self, model_output, timestep, sample, order: int = 1):
+        return self.fused_step(None, model_output, 1.0, False, timestep, sample)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 1
+#define FD_ABI_VERSION 2
 
 /* error codes */
 #define FD_OK            0
@@ -145,7 +145,17 @@ typedef struct fd_tween_params {
   double header_max;        /* Tweener.header_max        guidance.py:211 */
   int    align_mode;        /* FD_GUIDE_ORDER_*          guidance.py:212 */
   int    mapping_reuse;     /* bool                      guidance.py:213 */
+  int    blend_mode;        /* FD_BLEND_MODE_*: 0 = the reference's lerp (guidance.py:271);
+                               1 = per-token slerp for the rows the reference lerps
+                               (extension named by BASELINE.json north_star; the reference
+                               has no slerp, so this mode's parity is pinned to
+                               oracle/guidance_oracle.py:slerp_rows only)                 */
+  int    reserved;          /* must be 0 */
 } fd_tween_params;
+
+#define FD_BLEND_MODE_LERP  0
+#define FD_BLEND_MODE_SLERP 1
+#define FD_SLERP_DOT_THRESHOLD 0.9995f  /* |cos| above this falls back to lerp */
 
 int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddings             */
                  const float* guide_dev,     /* [guide_batch, A, D] fp32 alt embeddings          */

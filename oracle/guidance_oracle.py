@@ -158,6 +158,31 @@ class TweenParams:
     header_max: float = 0.15
     align_mode: int = GUIDE_ORDER_ALIGN
     mapping_reuse: bool = True
+    slerp: bool = False  # extension, NOT a reference argument (see slerp_rows)
+
+
+SLERP_DOT_THRESHOLD = 0.9995
+
+
+def slerp_rows(base_rows: torch.Tensor, alt_rows: torch.Tensor,
+               iw: np.ndarray) -> Tuple[torch.Tensor, np.ndarray, np.ndarray]:
+    '''EXTENSION -- parity unpinned: the reference has no slerp (its only blend
+    is the lerp at guidance.py:271); BASELINE.json's north_star names an optional
+    one, so this states the usual per-vector spherical interpolation it is checked
+    against: out = sin((1-w)O)/sin(O) * base + sin(wO)/sin(O) * alt with
+    O = acos(<base,alt>/(|base||alt|)); rows with |cos O| > 0.9995 keep the lerp.
+    Returns (rows [T,D] float64, used_slerp [T] bool, cos [T]).'''
+    b = base_rows.double().numpy()
+    a = alt_rows.double().numpy()
+    den = np.linalg.norm(b, axis=1) * np.linalg.norm(a, axis=1)
+    cosv = np.where(den > 0, (b * a).sum(1) / np.where(den > 0, den, 1), 1.0)
+    use = np.abs(cosv) <= SLERP_DOT_THRESHOLD
+    theta = np.arccos(np.clip(cosv, -1, 1))
+    st = np.where(use, np.sin(theta), 1.0)
+    ca = np.sin(theta - theta * iw) / st
+    cb = np.sin(theta * iw) / st
+    out = ca[:, None] * b + cb[:, None] * a
+    return torch.from_numpy(out), use, cosv
 
 
 def tween_weights(mapped: np.ndarray, prm: TweenParams) -> torch.Tensor:
@@ -212,6 +237,10 @@ def tween(base_emb: torch.Tensor,
     base_rows = base_emb[0]
     lerp = base_rows + (alt_rows - base_rows) * torch.tensor(
         iw, dtype=torch.float64).to(base_emb.dtype)[:, None]
+    if prm.slerp:
+        sl, use, _ = slerp_rows(base_rows, alt_rows, iw)
+        lerp = torch.where(torch.from_numpy(use)[:, None],
+                           sl.to(base_emb.dtype), lerp)
     sel_t = torch.from_numpy(sel)[:, None]
     out[0] = torch.where(sel_t == 0, base_rows,
                          torch.where(sel_t == 1, alt_rows, lerp))

@@ -27,6 +27,7 @@ def to_native_params(native, prm: orc.TweenParams):
     p.header_max = prm.header_max
     p.align_mode = prm.align_mode
     p.mapping_reuse = int(prm.mapping_reuse)
+    p.blend_mode = 1 if prm.slerp else 0
     return p
 
 

@@ -22,7 +22,7 @@ def test_header_symbols_all_exported(native):
 
 def test_struct_layouts_match_header(native):
     assert ctypes.sizeof(native.SchedCoeffs) == 40
-    assert ctypes.sizeof(native.TweenParams) == 48
+    assert ctypes.sizeof(native.TweenParams) == 56
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason='CPU-only behaviour')

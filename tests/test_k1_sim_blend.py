@@ -118,6 +118,51 @@ def test_identical_embeddings_saturate(native, cuda_dev):
             kc.check_exact_given_P(res, 0, 0, txt, txt, prm)
 
 
+def test_slerp_extension(native, cuda_dev):
+    '''FD_BLEND_MODE_SLERP: decisions (map, weights, select) stay bit-exact given the
+    kernel's P; rows the reference lerps are spherically interpolated instead.  The reference
+    has no slerp (parity unpinned): the check is oracle/guidance_oracle.py:slerp_rows, in
+    float64, so the tolerance below is fp32 sin/acos error (<= 2e-5 relative to the row's
+    largest element), and rows within 1e-4 of the |cos| = 0.9995 switch may use either form.'''
+    txt, img = orc.synthetic_pair(11)
+    prms = [orc.TweenParams(clustered=0.0, slerp=True),
+            orc.TweenParams(clustered=0.0, slerp=False),
+            orc.TweenParams(clustered=0.0, slerp=True, linear=(-0.3, 0.4),
+                            threshold=(0.2, 0.3), align_mode=0,
+                            mapping_reuse=False)]
+    res = kc.run_kernel(native, cuda_dev, txt, img, prms)
+    P = res['sim'][0]
+    n_slerp = 0
+    for p, prm in enumerate(prms):
+        want = kc.oracle_from_P(P, txt, img, prm)
+        assert not want['zde']
+        assert np.array_equal(res['map_idx'][0, p].numpy(),
+                              want['mapped'][:, 0].astype(np.int64))
+        assert torch.equal(res['weights'][0, p], want['w'])
+        got = res['out'][0, p]
+        if not prm.slerp:
+            assert torch.equal(got, want['out'])
+            continue
+        idx = torch.from_numpy(want['mapped'][:, 0].astype(np.int64))
+        sl, use, cosv = orc.slerp_rows(txt[0], img[0, idx], want['iw'])
+        for r in range(txt.shape[1]):
+            if want['sel'][r] != 2:
+                assert torch.equal(got[r], want['out'][r]), r
+                continue
+            scale = max(txt[0, r].abs().max().item(),
+                        img[0, idx[r]].abs().max().item())
+            d_sl = (got[r].double() - sl[r]).abs().max().item()
+            d_lerp = (got[r].double() - want['out'][r].double()).abs().max().item()
+            near = abs(abs(cosv[r]) - orc.SLERP_DOT_THRESHOLD) < 1e-4
+            if use[r] or near:
+                ok = d_sl <= 2e-5 * scale
+                n_slerp += int(ok and use[r])
+            if not use[r] or near:
+                ok = (d_lerp == 0.0) or (near and ok)
+            assert ok, (p, r, d_sl, d_lerp, cosv[r])
+    assert n_slerp >= 5  # the mode really ran
+
+
 def test_rejects_bad_shapes(native, cuda_dev):
     txt = torch.zeros(1, 77, 100, device=cuda_dev)  # D not a multiple of 32
     img = torch.zeros(1, 257, 100, device=cuda_dev)

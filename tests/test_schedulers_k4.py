@@ -78,3 +78,22 @@ def test_lms_scaled_model_input(native, cuda_dev):
     out = ps.fused_step(None, eps, 1.0, False, 0, x, scaled_out=scaled).prev_sample
     want = out / (ps.sigmas[1].item()**2 + 1)**0.5
     torch.testing.assert_close(scaled.float(), want, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize('steps,t_start', [(50, 0), (30, 12)])
+def test_euler_is_lms_order_1(native, cuda_dev, steps, t_start):
+    '''EulerDiscreteScheduler (extension; diffusers 0.3.0 has none) == the oracle's LMS
+    restatement stepped with order=1, same 2e-5 chained tolerance.'''
+    ps, os_ = prod.EulerDiscreteScheduler(), lo.LMSDiscreteScheduler()
+    ps.set_timesteps(steps)
+    os_.set_timesteps(steps)
+    g = torch.Generator().manual_seed(steps)
+    x = torch.randn(2, 4, 64, 64, generator=g) * os_.sigmas[0]
+    xp, xo = x.to(cuda_dev), x.clone()
+    for i in range(t_start, steps):
+        u = torch.randn(2, 4, 64, 64, generator=g)
+        c = torch.randn(2, 4, 64, 64, generator=g)
+        xo = os_.step(u + 7.5 * (c - u), i, xo, order=1).prev_sample
+        xp = ps.fused_step(u.to(cuda_dev), c.to(cuda_dev), 7.5, True, i,
+                           xp).prev_sample
+        assert ((xp.cpu() - xo).abs().max() / xo.abs().max()).item() < 2e-5
