@@ -7,6 +7,7 @@ Torch is used solely for device memory, streams and dtype bookkeeping.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional, Sequence
 
@@ -78,11 +79,14 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    lib_path = LIB_PATH
+    if os.environ.get('FD_LIB_PATH'):  # development aid: A/B a variant build (profiles/build_variants.py)
+        lib_path = Path(os.environ['FD_LIB_PATH'])
+    if not lib_path.exists():
         raise NativeError(
-            f'{LIB_PATH} is not built. Run `python -m flexdiffuse_b200.build` '
+            f'{lib_path} is not built. Run `python -m flexdiffuse_b200.build` '
             '(needs nvcc). flexdiffuse_b200 has no CPU / PyTorch fallback.')
-    l = C.CDLL(str(LIB_PATH))
+    l = C.CDLL(str(lib_path))
     l.fd_version.restype = C.c_int
     l.fd_last_error_string.restype = C.c_char_p
     l.fd_arch_check.argtypes = [C.c_int]

@@ -23,11 +23,12 @@ _native.cfg_sched_step(u.bfloat16(), c.bfloat16(), x, k, torch.empty_like(x), ep
 ctx = rn(160, 128).bfloat16()
 w = rn(328, 128).bfloat16()
 kv = _native.kv_project(ctx, w)
-# K3 (d = 40 and 160; partial query tile)
-for C, nq in ((320, 200), (1280, 64)):
-    q = rn(2, nq, C).bfloat16()
+# K3 (d = 40, 80, 160; partial query tile; 48 samples -> one CTA walks 6 tiles with both warpgroups,
+# the Q ring wraps and the in-place output staging is reused)
+for C, nq, S in ((320, 200, 2), (1280, 64, 2), (320, 768, 48), (640, 640, 48)):
+    q = rn(S, nq, C).bfloat16()
     kvc = rn(160, 2 * C).bfloat16()
-    _native.cross_attn(q, kvc, 0, C, torch.tensor([1, 0], dtype=torch.int32, device=dev), 8, 77, 80,
+    _native.cross_attn(q, kvc, 0, C, (torch.arange(S, dtype=torch.int32, device=dev) + 1) % 2, 8, 77, 80,
                        (C // 8)**-0.5)
 # K1 (257 guide tokens: TMA + remainder row; all modes)
 txt, img = rn(2, 77, 64), rn(1, 257, 64)

@@ -42,6 +42,54 @@ def test_k3_matches_torch(native, cuda_dev, n_q, C):
     torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
 
 
+@pytest.mark.parametrize('S', [1, 2, 16, 40])
+@pytest.mark.parametrize('n_q,C', [(4096, 320), (1024, 640), (1024, 1280),
+                                   (300, 640)])
+def test_k3_tile_walk(native, cuda_dev, S, n_q, C):
+    '''The sample count changes how many query tiles one CTA walks (1 ... 16, odd and even,
+    ragged last tile), which is what the two alternating softmax warpgroups, the Q ring and the
+    O-accumulator hand-off depend on.  Values differ per tile so a swapped tile is caught.'''
+    heads = 8
+    g = torch.Generator().manual_seed(S * n_q + C)
+    q = torch.randn(S, n_q, C, generator=g).to(cuda_dev).bfloat16()
+    kv = torch.randn(3 * T_PAD, 2 * C, generator=g).to(cuda_dev).bfloat16()
+    ctx_index = (torch.arange(S, dtype=torch.int32) % 3).to(cuda_dev)
+    scale = (C // heads)**-0.5
+    out = native.cross_attn(q, kv, 0, C, ctx_index, heads, T_VALID, T_PAD, scale)
+    torch.cuda.synchronize()
+    ref = _ref(q, kv, 0, C, ctx_index.tolist(), heads, scale)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize('C', [320, 640, 1280])
+def test_k3_every_key_position(native, cuda_dev, C):
+    '''Each query row is aligned with one key (row r -> key r % 77) at three sharpness levels, so
+    every key column carries the weight for some row: part of the columns take 2^x from the FMA-pipe
+    polynomial and part from MUFU.EX2, and both must stay inside the same 2e-2 tolerance.  The soft
+    rows (gain 0.5, many keys contribute) would expose a systematic bias between the two paths.'''
+    heads, n_q = 8, 3 * 77
+    d = C // heads
+    g = torch.Generator().manual_seed(C)
+    kv = torch.randn(T_PAD, 2 * C, generator=g).bfloat16()
+    k = kv[:T_VALID, :C].float().view(T_VALID, heads, d)
+    q = torch.empty(1, n_q, C)
+    for r in range(n_q):
+        gain = (0.5, 2.0, 8.0)[r // 77]
+        q[0, r] = (gain * k[r % 77]).reshape(C)
+    q = q.to(cuda_dev).bfloat16()
+    kv = kv.to(cuda_dev)
+    ctx_index = torch.zeros(1, dtype=torch.int32, device=cuda_dev)
+    scale = d**-0.5
+    out = native.cross_attn(q, kv, 0, C, ctx_index, heads, T_VALID, T_PAD, scale)
+    torch.cuda.synchronize()
+    ref = _ref(q, kv, 0, C, [0], heads, scale)
+    torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    # the sharp rows reproduce "their" value row
+    v = kv[:T_VALID, C:].float()
+    sharp = out[0, 2 * 77:].float()
+    assert (sharp - v).abs().max() < 5e-2
+
+
 def test_k3_peaked_softmax(native, cuda_dev):
     '''Large logits: softmax must stay finite and pick the dominant key.'''
     heads, C, n_q = 8, 320, 128
