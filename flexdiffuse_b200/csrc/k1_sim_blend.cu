@@ -285,7 +285,20 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     float ssb[B_ITEMS];
 #pragma unroll
     for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
+    // A single remainder guide row (A = 257: the usual case) is folded into this loop: the thread
+    // already holds 4 consecutive floats of its text rows for every chunk, so the exact-fp32 dot
+    // product with the row's matching 4 floats costs one cached load + 4 FMAs per item instead of a
+    // separate, latency-bound pass after the GEMM feed (it was ~16 us of a 78 us CTA).
+    const int n_rem = A - a.a_mma;
+    const bool fold_rem = n_rem == 1;
+    const float* grem = a.guide + (static_cast<size_t>(g_idx) * A + a.a_mma) * D + (tt & 7) * 4;
+    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float racc[B_ITEMS];
+#pragma unroll
+    for (int j = 0; j < B_ITEMS; ++j) racc[j] = 0.f;
+    static_assert(TEXT_THREADS % 8 == 0, "all items of a thread share the same 4-float column slice");
     auto load_chunk = [&](int kc) {
+      if (fold_rem) gq = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
 #pragma unroll
       for (int j = 0; j < B_ITEMS; ++j) {
         const int f = tt + j * TEXT_THREADS;
@@ -319,6 +332,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           *reinterpret_cast<float4*>(t_hi + off) = h;
           *reinterpret_cast<float4*>(t_lo + off) = l;
           ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          racc[j] = fmaf(v.x, gq.x, fmaf(v.y, gq.y, fmaf(v.z, gq.z, fmaf(v.w, gq.w, racc[j]))));
         }
       }
       fence_proxy_async_smem();
@@ -333,13 +347,19 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      float rs = racc[j];
+      rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+      rs += __shfl_xor_sync(0xffffffffu, rs, 4);
       const int f = tt + j * TEXT_THREADS;
-      if ((f & 7) == 0 && (f >> 3) < NPAD) sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
+      if ((f & 7) == 0 && (f >> 3) < NPAD) {
+        sm.inv_norm_b[f >> 3] = 1.0f / sqrtf(ss);
+        if (fold_rem) sm.rem[0][f >> 3] = rs;
+      }
     }
     // remainder guide rows (A - a_mma <= 8) on the CUDA cores, exact fp32: warp w takes
     // text tokens w, w + 10, ...
-    const int n_rem = A - a.a_mma;
-    if (n_rem > 0) {
+    if (n_rem > 1) {
       const float* gr = a.guide + (static_cast<size_t>(g_idx) * A + a.a_mma) * D;
       for (int j = warp - 2; j < T; j += TEXT_WARPS) {
         float acc[MAX_REM];
@@ -375,19 +395,22 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 
   // ------------------------------------------------------------------ 2. logits -> smem, softmax per guide token
   {
-    // 2a. TMEM lane j (text token) -> row j of the logits matrix; 100 * cos in the log2 domain
-    if (warp < 4) {
-      const int j = warp * 32 + lane;
+    // 2a. TMEM lane j (text token) -> row j of the logits matrix; 100 * cos in the log2 domain.
+    // All 12 warps: the three warps that share a TMEM lane quarter (w, w+4, w+8) take 32-column
+    // blocks round-robin (only 4 warps did this before: 9 us of a 64 us CTA).
+    {
+      const int quarter = warp & 3, third = warp >> 2;
+      const int j = quarter * 32 + lane;
       const float sb = (j < T) ? sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) : 0.f;
-      for (int c0 = 0; c0 < a.a_mma; c0 += 64) {
-        uint32_t v[4][16];
+      for (int c0 = third * 32; c0 < a.a_mma; c0 += 3 * 32) {
+        uint32_t v[2][16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          if (c0 + 16 * g < n_pad) tmem_ld_x16(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0 + 16 * g, v[g]);
+        for (int g = 0; g < 2; ++g)
+          if (c0 + 16 * g < n_pad) tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0 + 16 * g, v[g]);
         tmem_ld_wait();
         if (j < T) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < 2; ++g)
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const int i = c0 + 16 * g + q;
@@ -396,13 +419,12 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         }
       }
       tc_fence_before();
-    } else {
       // remainder guide rows computed on the CUDA cores
       const int n_rem = A - a.a_mma;
-      for (int idx = tid - 128; idx < n_rem * T; idx += K1_THREADS - 128) {
-        const int r = idx / T, j = idx - r * T;
-        pt_full[j * PT_STRIDE + a.a_mma + r] =
-            sm.rem[r][j] * sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) * sm.inv_norm_a[a.a_mma + r];
+      for (int idx = tid; idx < n_rem * T; idx += K1_THREADS) {
+        const int r = idx / T, jj = idx - r * T;
+        pt_full[jj * PT_STRIDE + a.a_mma + r] =
+            sm.rem[r][jj] * sm.inv_norm_b[jj] * (100.0f * 1.4426950408889634f) * sm.inv_norm_a[a.a_mma + r];
       }
     }
     __syncthreads();
@@ -784,31 +806,46 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     {
       const int d4 = D / 4;
       float* outp = a.out + bp * T * D;
-      for (int idx = tid; idx < T * d4; idx += K1_THREADS) {
-        const int r = idx / d4, c = idx - r * d4;
-        const int sel = sm.sel[r];
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(r) * D) + c);
-        float4 o = bv;
-        if (sel != 0) {
-          const float4 av = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[r]) * D) + c);
-          if (sel == 1) {
-            o = av;
-          } else if (sel == 3) {
-            const float ca = sm.slerp_a[r], cb = sm.slerp_b[r];
-            o.x = __fadd_rn(__fmul_rn(ca, bv.x), __fmul_rn(cb, av.x));
-            o.y = __fadd_rn(__fmul_rn(ca, bv.y), __fmul_rn(cb, av.y));
-            o.z = __fadd_rn(__fmul_rn(ca, bv.z), __fmul_rn(cb, av.z));
-            o.w = __fadd_rn(__fmul_rn(ca, bv.w), __fmul_rn(cb, av.w));
-          } else {
-            const float w = sm.iw[r];
-            // base + (alt - base) * iw, every op rounded separately like the torch expression
-            o.x = __fadd_rn(bv.x, __fmul_rn(__fsub_rn(av.x, bv.x), w));
-            o.y = __fadd_rn(bv.y, __fmul_rn(__fsub_rn(av.y, bv.y), w));
-            o.z = __fadd_rn(bv.z, __fmul_rn(__fsub_rn(av.z, bv.z), w));
-            o.w = __fadd_rn(bv.w, __fmul_rn(__fsub_rn(av.w, bv.w), w));
+      constexpr int BU = 4;  // items in flight per thread (one at a time left the phase latency-bound)
+      for (int idx0 = tid; idx0 < T * d4; idx0 += BU * K1_THREADS) {
+        float4 bv[BU], av[BU];
+        int sel[BU], rr[BU], cc[BU];
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+          const int idx = idx0 + u * K1_THREADS;
+          sel[u] = -1;
+          if (idx < T * d4) {
+            rr[u] = idx / d4;
+            cc[u] = idx - rr[u] * d4;
+            sel[u] = sm.sel[rr[u]];
+            bv[u] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(rr[u]) * D) + cc[u]);
+            if (sel[u] != 0)
+              av[u] = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[rr[u]]) * D) + cc[u]);
           }
         }
-        __stcs(reinterpret_cast<float4*>(outp + static_cast<size_t>(r) * D) + c, o);
+#pragma unroll
+        for (int u = 0; u < BU; ++u) {
+          if (sel[u] < 0) continue;
+          const int r = rr[u];
+          float4 o = bv[u];
+          if (sel[u] == 1) {
+            o = av[u];
+          } else if (sel[u] == 3) {
+            const float ca = sm.slerp_a[r], cb = sm.slerp_b[r];
+            o.x = __fadd_rn(__fmul_rn(ca, bv[u].x), __fmul_rn(cb, av[u].x));
+            o.y = __fadd_rn(__fmul_rn(ca, bv[u].y), __fmul_rn(cb, av[u].y));
+            o.z = __fadd_rn(__fmul_rn(ca, bv[u].z), __fmul_rn(cb, av[u].z));
+            o.w = __fadd_rn(__fmul_rn(ca, bv[u].w), __fmul_rn(cb, av[u].w));
+          } else if (sel[u] == 2) {
+            const float w = sm.iw[r];
+            // base + (alt - base) * iw, every op rounded separately like the torch expression
+            o.x = __fadd_rn(bv[u].x, __fmul_rn(__fsub_rn(av[u].x, bv[u].x), w));
+            o.y = __fadd_rn(bv[u].y, __fmul_rn(__fsub_rn(av[u].y, bv[u].y), w));
+            o.z = __fadd_rn(bv[u].z, __fmul_rn(__fsub_rn(av[u].z, bv[u].z), w));
+            o.w = __fadd_rn(bv[u].w, __fmul_rn(__fsub_rn(av[u].w, bv[u].w), w));
+          }
+          __stcs(reinterpret_cast<float4*>(outp + static_cast<size_t>(r) * D) + cc[u], o);
+        }
       }
     }
     __syncthreads();
