@@ -249,10 +249,15 @@ def kernel_rooflines(dev, unet, peaks):
     f2()
     t = _time_cuda(f2, 10, flush)
     fl = 2 * 9 * 80 * 768 * 24960
+    # context only (never on the product path): the same GEMM through torch.matmul (cuBLAS), same
+    # timing method -- the tensor `peak` is measured on large cuBLAS GEMMs, this one is 17 us of it
+    f2c = lambda: torch.matmul(ctx9, unet._kv_weight.t(), out=kv9)
+    f2c()
+    t_cublas = _time_cuda(f2c, 10, flush)
     out['k2'] = dict(bound='tensor', achieved=fl / t / 1e12, peak=peaks['tensor'],
                      unit='TFLOP/s', frac=fl / t / 1e12 / peaks['tensor'], traffic=NCU_TRAFFIC_BYTES['k2'],
                      kernel='k2_gemm_kernel (M=720,N=24960,K=768; 9 contexts)',
-                     avg_launch_us=t * 1e6, peak_of=peaks['source'])
+                     avg_launch_us=t * 1e6, cublas_same_shape_us=t_cublas * 1e6, peak_of=peaks['source'])
     # ---- K1: blends/s -- 1024 prompts x 1 shared guide image, default parameters
     nb = 1024
     txt = torch.randn(nb, 77, 768, device=dev)

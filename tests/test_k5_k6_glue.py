@@ -10,7 +10,12 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize('N,C,H,W', [(2, 320, 64, 64), (2, 960, 32, 32),
                                      (4, 1280, 8, 8), (1, 2560, 16, 16),
-                                     (3, 640, 5, 7), (2, 1920, 32, 32)])
+                                     (3, 640, 5, 7), (2, 1920, 32, 32),
+                                     # cluster path with 1 / 2 / 4 groups per cluster (16-byte strips
+                                     # of 16..240 B), the VAE widths, and shapes that must stream
+                                     (1, 128, 64, 64), (1, 256, 32, 32), (2, 512, 16, 16),
+                                     (2, 640, 64, 64), (2, 960, 64, 64), (8, 320, 64, 64),
+                                     (2, 2560, 8, 8), (1, 512, 61, 3)])
 @pytest.mark.parametrize('silu,with_bias', [(True, False), (True, True),
                                             (False, False)])
 def test_groupnorm_act_matches_torch(native, cuda_dev, N, C, H, W, silu, with_bias):
