@@ -235,7 +235,25 @@ def kernel_rooflines(dev, unet, peaks):
     f4 = lambda: _native.cfg_sched_step(u, c, x, k, xo)
     f4()
     t = _time_cuda(f4, 20)
+    # ... and at the batch sizes the loop really runs: launch-bound, so graph-replayed
+    real_b = {}
+    for rb in (1, 8, 16):
+        m = rb * 4 * 64 * 64
+        g4 = torch.cuda.CUDAGraph()
+        fr = lambda: _native.cfg_sched_step(u[:m], c[:m], x[:m], k, xo[:m])
+        fr()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fr()
+        torch.cuda.current_stream().wait_stream(side)
+        with torch.cuda.graph(g4):
+            for _ in range(20):
+                fr()
+        g4.replay()
+        real_b[str(rb)] = round(_time_cuda(g4.replay, 5) / 20 * 1e6, 2)
     out['k4'] = dict(bound='hbm', achieved=16 * n / t / 1e9, peak=peaks['hbm'], unit='GB/s',
+                     us_per_step_at_batch=real_b,
                      frac=16 * n / t / 1e9 / peaks['hbm'], traffic=NCU_TRAFFIC_BYTES['k4'],
                      algorithmic_bytes_per_launch=16 * n,
                      kernel='k4_cfg_sched_kernel (DDIM, fp32, 1024 samples)',
