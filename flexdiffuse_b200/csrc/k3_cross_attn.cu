@@ -27,19 +27,12 @@
 // ~1 tile/us no matter how many warps it had.)  HBM-bound by design (AI = 77 FLOP/B).
 #include "fd_common.cuh"
 
-// tuning knobs (profiles/build_variants.py builds A/B libraries with -D overrides)
-#ifndef K3_PASS1_BATCH
-#define K3_PASS1_BATCH 0   // two-pass softmax, pass 1: 1 = two TMEM round trips (48 + 32 columns), 0 = five (measured: 0 is 3 % faster at 96 registers)
-#endif
-#ifndef K3_EARLY_LOADS
-#define K3_EARLY_LOADS 1   // first Q / K / V loads issued before the CTA-wide sync
-#endif
+// tuning knobs (profiles/build_variants.py builds A/B libraries with -D overrides); the variants that
+// lost their A/B -- FMA-pipe 2^x for part of the keys, pass-1 row max in two TMEM round trips, a
+// column-split one-pass softmax, a flat tile scheduler -- are recorded in profiles/r01/SUMMARY.md
 #ifndef K3_FIRST_TILES
 #define K3_FIRST_TILES 1   // Q tiles requested up front; the rest of the ring follows once tile 0 has landed
                            // (8 x 4096 x 320: 4 -> 17.2 us, 2 -> 16.6, 1 -> 16.4; 8 x 1024 x 640: 8.1 / 7.6 / 7.2)
-#endif
-#ifndef K3_POLY_PAIRS
-#define K3_POLY_PAIRS 0    // key pairs per 16-column step whose 2^x runs on the FMA pipe
 #endif
 #ifndef K3_QSTAGES_SMALL
 #define K3_QSTAGES_SMALL 4 // Q ring depth for d <= 128 (2: 19.6 us, 3: 17.6, 4: 17.0, 5: 17.5 at 8 x 4096 x 320)
@@ -54,10 +47,6 @@ constexpr int K3_THREADS = 320;
 constexpr int Q_CHUNK_BYTES = TQ * 128;
 constexpr int KV_CHUNK_BYTES = TKV * 128;
 constexpr int MAX_QSTAGES = 5;
-// of the 8 key pairs in a 16-column step, this many take 2^x on the FMA pipe (Cody-Waite split +
-// degree-3 minimax polynomial, max rel. error 8.6e-5, 45x below the bf16 rounding of P) instead of
-// MUFU.EX2: the softmax phase is MUFU-bound (16 lanes/clk/SM) while the FMA pipe idles
-constexpr int POLY_PAIRS = K3_POLY_PAIRS;  // measured: no gain at 3 (the phase is not MUFU-bound)
 
 template <int DH>
 struct K3Cfg {
@@ -193,8 +182,8 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
       tma_load_3d(sv + c * KV_CHUNK_BYTES, &tm_v, kv_full, c * 64, head, ctx_row);
     }
   };
-  // K3_EARLY_LOADS: the first loads go out while warp 1 allocates TMEM and the CTA synchronises
-  if (K3_EARLY_LOADS && threadIdx.x == 0) first_loads();
+  // the first loads go out while warp 1 allocates TMEM and the CTA synchronises (2-3 % per launch)
+  if (threadIdx.x == 0) first_loads();
   if (warp == 1) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
@@ -208,7 +197,6 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (threadIdx.x == 0) {
-      if (!K3_EARLY_LOADS) first_loads();
       auto store_tile = [&](int j) {  // output of tile j: staged by its warpgroup -> TMA store
         const int s = j % QS;
         mbar_wait(&out_full[s], (j / QS) & 1);
@@ -342,9 +330,6 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     };
 
     const uint64_t scale2 = f2_pack(a.scale_log2e, a.scale_log2e);
-    const uint64_t magic2 = f2_pack(12582912.f, 12582912.f), one2 = f2_pack(1.f, 1.f);
-    const uint64_t pc1 = f2_pack(0.69511657f, 0.69511657f), pc2 = f2_pack(0.22764593f, 0.22764593f),
-                   pc3 = f2_pack(0.07706618f, 0.07706618f);
     for (int i = wg; i < my_tiles; i += 2) {
       if (stamp) K3_EVENT(i, 2);  // group starts waiting for S
       mbar_wait(&s_full[wg], (i >> 1) & 1);
@@ -387,39 +372,6 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           tmem_st_x8(sbuf + 8 * c, pk);
         }
       } else {
-#if K3_PASS1_BATCH
-        // ---- pass 1: row max over the 80 logits in two TMEM round trips (48 + 32 columns)
-        float mx;
-        {
-          uint32_t va[3][16], vb[2][16];
-#pragma unroll
-          for (int c = 0; c < 3; ++c) tmem_ld_x16(sbuf + 16 * c, va[c]);
-          tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 2; ++c) tmem_ld_x16(sbuf + 48 + 16 * c, vb[c]);
-          float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              m0 = fmax3(m0, __uint_as_float(va[c][j]), __uint_as_float(va[c][j + 1]));
-              m1 = fmax3(m1, __uint_as_float(va[c][j + 2]), __uint_as_float(va[c][j + 3]));
-            }
-          tmem_ld_wait();
-          // keys >= t_valid only exist in the last 16 columns (t_valid > 64 is checked on the host)
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (TKV - 16 + j >= a.t_valid) vb[1][j] = 0xff800000u;  // -inf
-#pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              m0 = fmax3(m0, __uint_as_float(vb[c][j]), __uint_as_float(vb[c][j + 1]));
-              m1 = fmax3(m1, __uint_as_float(vb[c][j + 2]), __uint_as_float(vb[c][j + 3]));
-            }
-          mx = fmaxf(m0, m1);
-        }
-#else
         // ---- pass 1: row max over the 80 logits, 16 columns per step, next load in flight
         float mx;
         {
@@ -446,7 +398,6 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
           }
           mx = fmaxf(m0, m1);
         }
-#endif
         // ---- pass 2: exp2(s * scale*log2e - max * scale*log2e) (one FFMA2 per two keys + one MUFU per
         // key; scale > 0), row sum, bf16 P stored over S; 16 columns per step, next load in flight
         const float nmx = -mx * a.scale_log2e;
@@ -454,37 +405,21 @@ k3_cross_attn_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
         {
           uint32_t v[2][16];
           tmem_ld_x16(sbuf, v[0]);
-  #pragma unroll
+#pragma unroll
           for (int c = 0; c < TKV / 16; ++c) {
             tmem_ld_wait();
             if (c + 1 < TKV / 16) tmem_ld_x16(sbuf + 16 * (c + 1), v[(c + 1) & 1]);
             uint32_t pk[8];
-  #pragma unroll
+#pragma unroll
             for (int k = 0; k < 8; ++k) {
               float x0 = __uint_as_float(v[c & 1][2 * k]), x1 = __uint_as_float(v[c & 1][2 * k + 1]);
               if (c == TKV / 16 - 1) {
                 if (16 * c + 2 * k >= a.t_valid) x0 = -INFINITY;
                 if (16 * c + 2 * k + 1 >= a.t_valid) x1 = -INFINITY;
               }
-              float t0, t1, e0, e1;
+              float t0, t1;
               f2_unpack(f2_fma(f2_pack(x0, x1), scale2, nmx2), t0, t1);
-              if (k < POLY_PAIRS) {
-                // x = n + f, n = floor(x) (round-down add of 1.5 * 2^23), f in [0,1): 2^x = p(f) << n
-                const uint64_t xc = f2_pack(fmaxf(t0, -126.f), fmaxf(t1, -126.f));
-                const uint64_t tt = f2_add_rm(xc, magic2);
-                const uint64_t fr = f2_sub(xc, f2_sub(tt, magic2));
-                uint64_t pl = f2_fma(pc3, fr, pc2);
-                pl = f2_fma(pl, fr, pc1);
-                pl = f2_fma(pl, fr, one2);
-                float p0, p1, n0, n1;
-                f2_unpack(pl, p0, p1);
-                f2_unpack(tt, n0, n1);
-                e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(n0) << 23));
-                e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(n1) << 23));
-              } else {
-                e0 = ex2_approx(t0);
-                e1 = ex2_approx(t1);
-              }
+              const float e0 = ex2_approx(t0), e1 = ex2_approx(t1);
               if (k & 1) acc1 = f2_add(acc1, f2_pack(e0, e1));
               else acc0 = f2_add(acc0, f2_pack(e0, e1));
               pk[k] = pack_bf16x2(e0, e1);
