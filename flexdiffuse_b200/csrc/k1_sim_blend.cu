@@ -33,7 +33,8 @@
 namespace fd {
 namespace {
 
-constexpr int K1_THREADS = 384;
+constexpr int K1_THREADS = 256;   // 128 registers x 256 threads: two CTAs per SM, so one prompt's softmax / mapping /
+                                  // blend tail overlaps the other's GEMM (384 threads x 168 registers allowed one)
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int NPAD = 80;          // UMMA N (text tokens padded)
 constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
@@ -42,10 +43,10 @@ constexpr int TXT_TILE_BYTES = 128 * 128;  // M operand: 128 rows (80 used) x 12
 constexpr int MAX_A = MAX_TILES * 128;     // 384 guide tokens
 constexpr int MAX_REM = 8;        // guide rows past the last multiple of 16 that go to the CUDA cores
 constexpr int TEXT_WARPS = K1_WARPS - 2;
-constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 320
-constexpr int PT_STRIDE = MAX_A + 1;   // floats per P^T row; odd => conflict-free row-per-lane stores
+constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 192
+constexpr int PT_STRIDE_MAX = MAX_A + 1;   // floats per P^T row: A | 1 (odd => conflict-free row-per-lane stores)
 constexpr int MAXT = 80;
-constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 2
+constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 4
 
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
@@ -66,6 +67,7 @@ struct K1Args {
   const float* guide;    // [guide_batch, A, D]
   const float* inv_norm_a;  // [guide_batch, A] from the prep kernel
   int a_mma, n_pad, n_stages;  // guide rows on the tensor cores, padded to 16, pipeline depth
+  int pt_stride, stage_area;   // floats per logits row (A | 1); bytes of the staging / logits area before K1Smem
   int n_text, guide_batch, T, A, D;
   const fd_tween_params* params;  // device [n_params]
   const float* lin_w;             // device [n_params, T]
@@ -97,10 +99,12 @@ struct K1Smem {
   uint32_t tmem_slot;
 };
 
-constexpr int K1_STAGE_AREA = 2 * (2 * TXT_TILE_BYTES + 2 * 256 * 128);  // 196,608: two stages at A <= 256
-static_assert(K1_STAGE_AREA >= 2 * TXT_TILE_BYTES + 2 * MAX_A * 128, "one stage at A = 384 must fit");
-static_assert(K1_STAGE_AREA >= MAXT * PT_STRIDE * 4, "the logits / P^T matrix aliases the stage area");
-constexpr int K1_SMEM_BYTES = 1024 + K1_STAGE_AREA + sizeof(K1Smem);
+// shared memory = 1024 (alignment) + stage area + K1Smem; the stage area holds n_stages operand stages during
+// the GEMM and the [T][A | 1] logits / P^T matrix afterwards.  A <= 256: ONE stage of 96 KB (the second CTA on
+// the SM is what keeps the tensor pipe fed while this one loads) -> ~107 KB per CTA, two CTAs per SM.
+constexpr int K1_MAX_STAGE_AREA = 2 * TXT_TILE_BYTES + 2 * MAX_A * 128;  // one stage at A = 384
+static_assert(K1_MAX_STAGE_AREA >= MAXT * PT_STRIDE_MAX * 4, "the logits / P^T matrix fits the largest stage area");
+constexpr int K1_MAX_SMEM_BYTES = 1024 + K1_MAX_STAGE_AREA + sizeof(K1Smem);
 
 __device__ __forceinline__ void argmax_combine(float& s, int& i, float os, int oi) {
   // larger s wins, ties -> lower index; index < 0 means "nothing"
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restr
   if (lane == 0) inv_norm[row] = 1.0f / sqrtf(ss);
 }
 
-__global__ void __launch_bounds__(K1_THREADS, 1)
+__global__ void __launch_bounds__(K1_THREADS, 2)
 k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                     const __grid_constant__ CUtensorMap tm_hi2, const __grid_constant__ CUtensorMap tm_lo2,
                     const K1Args a) {
@@ -188,9 +192,10 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   const int n_pad = a.n_pad;
   const uint32_t g_plane = static_cast<uint32_t>(n_pad) * 128u;
   const uint32_t stage_bytes = 2u * TXT_TILE_BYTES + 2u * g_plane;
+  const int PT_STRIDE = a.pt_stride;
   float* pt_full = reinterpret_cast<float*>(stage);  // [T][PT_STRIDE] logits, then probabilities
   float* pt = pt_full + PT_STRIDE;  // row r <-> text token r + 1 (header row dropped, guidance.py:55)
-  K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + K1_STAGE_AREA);
+  K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + a.stage_area);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -396,13 +401,13 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   // ------------------------------------------------------------------ 2. logits -> smem, softmax per guide token
   {
     // 2a. TMEM lane j (text token) -> row j of the logits matrix; 100 * cos in the log2 domain.
-    // All 12 warps: the three warps that share a TMEM lane quarter (w, w+4, w+8) take 32-column
-    // blocks round-robin (only 4 warps did this before: 9 us of a 64 us CTA).
+    // All warps: the warps that share a TMEM lane quarter (w, w+4, ...) take 32-column blocks
+    // round-robin (only 4 warps did this before: 9 us of a 64 us CTA).
     {
-      const int quarter = warp & 3, third = warp >> 2;
+      const int quarter = warp & 3, third = warp >> 2;  // K1_WARPS / 4 warps share a TMEM lane quarter
       const int j = quarter * 32 + lane;
       const float sb = (j < T) ? sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) : 0.f;
-      for (int c0 = third * 32; c0 < a.a_mma; c0 += 3 * 32) {
+      for (int c0 = third * 32; c0 < a.a_mma; c0 += (K1_WARPS / 4) * 32) {
         uint32_t v[2][16];
 #pragma unroll
         for (int g = 0; g < 2; ++g)
@@ -924,7 +929,15 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   a.inv_norm_a = g_inv;
   a.a_mma = a_mma;
   a.n_pad = n_pad;
-  a.n_stages = (2 * (2 * TXT_TILE_BYTES + 2 * n_pad * 128) <= K1_STAGE_AREA) ? 2 : 1;
+  a.n_stages = 1;
+  a.pt_stride = A | 1;
+  {
+    int64_t area = 2 * TXT_TILE_BYTES + 2 * static_cast<int64_t>(n_pad) * 128;  // one operand stage
+    const int64_t logits = static_cast<int64_t>(MAXT) * a.pt_stride * 4;
+    if (logits > area) area = logits;
+    a.stage_area = static_cast<int>((area + 127) / 128 * 128);
+  }
+  const int smem_bytes = 1024 + a.stage_area + static_cast<int>(sizeof(K1Smem));
   a.text = text_dev;
   a.guide = guide_dev;
   a.n_text = n_text;
@@ -951,9 +964,9 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   a.params_per_cta = (n_params + chunks - 1) / chunks;
   chunks = (n_params + a.params_per_cta - 1) / a.params_per_cta;
   FD_REQUIRE(chunks <= 65535, "fd_sim_blend: too many parameter chunks");
-  FD_CUDA_OK(cudaFuncSetAttribute(k1_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_SMEM_BYTES));
+  FD_CUDA_OK(cudaFuncSetAttribute(k1_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K1_MAX_SMEM_BYTES));
   dim3 grid(n_text, chunks);
-  k1_sim_blend_kernel<<<grid, K1_THREADS, K1_SMEM_BYTES, cst>>>(tm_hi, tm_lo, tm_hi2, tm_lo2, a);
+  k1_sim_blend_kernel<<<grid, K1_THREADS, smem_bytes, cst>>>(tm_hi, tm_lo, tm_hi2, tm_lo2, a);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }
