@@ -216,15 +216,20 @@ __device__ __forceinline__ uint32_t cluster_nctarank() {
   asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
   return r;
 }
+// split barrier used only to know that every CTA of the cluster has STARTED (its shared memory may be
+// written remotely after that): arrive at kernel entry, wait right before the first remote store
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ float2 dsmem_ld_f2(const float2* local_ptr, uint32_t rank) {
+// store into the same shared-memory variable of CTA `rank` of this cluster
+__device__ __forceinline__ void dsmem_st_f2(float2* local_ptr, uint32_t rank, float2 v) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
-  float2 v;
-  asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(remote) : "memory");
-  return v;
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(v.x), "f"(v.y) : "memory");
 }
 
 constexpr int GN_MAX_GSET = 8;    // groups per cluster
@@ -233,9 +238,10 @@ constexpr int GN_MAX_SV = 32;     // 16-byte vectors per pixel strip (<= 512 B)
 __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClusterArgs a) {
   extern __shared__ uint4 slab[];                      // [rows_per_cta][sv]
   __shared__ float2 s_col[GN_THREADS * 4];             // [RP][sv * 4] pair-column partials, tree-reduced over RP
-  __shared__ float2 cta_partial[GN_MAX_GSET];
+  __shared__ float2 all_partial[8][GN_MAX_GSET];       // [cluster rank][group]: every CTA's partials, pushed by the peers
   __shared__ float2 s_stats[GN_MAX_GSET];
   const uint32_t crank = cluster_ctarank(), csize = cluster_nctarank();
+  cluster_arrive_relaxed();
   const int sets = a.G / a.gset;
   const int set_id = blockIdx.x / csize;  // (n, group set) flattened
   const int n = set_id / sets, gs = set_id - n * sets;
@@ -301,6 +307,7 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
     }
     __syncthreads();
   }
+  cluster_wait();  // every peer is running (it arrived at entry); normally long satisfied by now
   if (tid < a.gset) {
     float ss = 0.f, qq = 0.f;
     for (int k = 0; k < cg2; ++k) {
@@ -308,19 +315,18 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
       ss += v.x;
       qq += v.y;
     }
-    cta_partial[tid] = make_float2(ss, qq);
+    // push model: write this CTA's partials into every peer's shared memory (and its own), so that
+    // after the barrier each CTA only reads locally and nobody has to wait for its peers before
+    // exiting (a pull model needs a second cluster barrier at the end of the kernel)
+    const float2 mine = make_float2(ss, qq);
+    for (uint32_t r = 0; r < csize; ++r) dsmem_st_f2(&all_partial[crank][tid], r, mine);
   }
-  cluster_sync_all();  // every CTA's partials are visible cluster-wide
+  cluster_sync_all();  // release / acquire: every CTA's partials have landed everywhere
   if (tid < a.gset) {
-    float2 t[8];
-#pragma unroll
-    for (uint32_t r = 0; r < 8; ++r)  // independent remote loads, all in flight
-      t[r] = r < csize ? dsmem_ld_f2(&cta_partial[tid], r) : make_float2(0.f, 0.f);
     float ts = 0.f, tq = 0.f;
-#pragma unroll
-    for (uint32_t r = 0; r < 8; ++r) {  // same order on every CTA => identical statistics
-      ts += t[r].x;
-      tq += t[r].y;
+    for (uint32_t r = 0; r < csize; ++r) {  // same order on every CTA => identical statistics
+      ts += all_partial[r][tid].x;
+      tq += all_partial[r][tid].y;
     }
     const float cnt = static_cast<float>(a.HW) * cg;
     const float mean = ts / cnt;
@@ -359,7 +365,6 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
       yb[static_cast<size_t>(r) * vec_per_row] = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
-  cluster_sync_all();  // nobody exits while a peer may still be reading its partials
 }
 
 // K7: y = x + h + bias[c]   (residual add with the convolution bias folded in), NHWC bf16
