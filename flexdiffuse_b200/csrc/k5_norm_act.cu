@@ -511,6 +511,7 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y_bf16_dev);
   const int64_t total_bytes = static_cast<int64_t>(N) * HW * C * 2;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  constexpr int64_t gn_min_cta_bytes = 4096;  // measured: 0 / 4 / 8 KB within 0.1 us, 20 KB and more slower
   static const int64_t cluster_max = [] {  // development override of the path switch
     const char* e = getenv("FD_GN_CLUSTER_MAX_BYTES");
     return e ? static_cast<int64_t>(atoll(e)) : GN_CLUSTER_MAX_BYTES;
@@ -525,7 +526,8 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
       const int64_t set_bytes = static_cast<int64_t>(HW) * sv * 16;
       const int64_t n_sets = static_cast<int64_t>(N) * (G / gset);
       int cl = 1;
-      while (cl < 8 && (set_bytes / cl > 64 * 1024 || n_sets * cl < sm_count())) cl *= 2;
+      // do not split a strip below 4 KB per CTA just to fill the SMs: a wider cluster barrier costs more
+      while (cl < 8 && (set_bytes / cl > 64 * 1024 || (n_sets * cl < sm_count() && set_bytes / cl > gn_min_cta_bytes))) cl *= 2;
       while (cl > 1 && HW < cl * 8) cl /= 2;
       const int rows_per_cta = (HW + cl - 1) / cl;
       const int64_t smem = static_cast<int64_t>(rows_per_cta) * sv * 16;
