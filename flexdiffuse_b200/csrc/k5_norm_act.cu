@@ -404,9 +404,19 @@ __global__ void __launch_bounds__(256) k8_add_layernorm_kernel(const uint32_t* _
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const uint32_t* xr = x + row * PAIRS;
-  uint32_t xv[PAIRS_PER_LANE], yv[PAIRS_PER_LANE];
+  uint32_t xv[PAIRS_PER_LANE], yv[PAIRS_PER_LANE], gv[PAIRS_PER_LANE], bv[PAIRS_PER_LANE];
 #pragma unroll
   for (int i = 0; i < PAIRS_PER_LANE; ++i) xv[i] = xr[lane + 32 * i];
+  // gamma / beta are only needed after both reductions: ask for them now so their latency hides there
+  // (few-row launches, C >= 640: 4.2 -> 2.9 us; at C = 320 with 8192 rows the later load is 0.2 us faster)
+  constexpr bool HOIST = PAIRS_PER_LANE >= 10;
+  if constexpr (HOIST) {
+#pragma unroll
+    for (int i = 0; i < PAIRS_PER_LANE; ++i) {
+      gv[i] = gamma[lane + 32 * i];
+      bv[i] = beta[lane + 32 * i];
+    }
+  }
   if (y) {
     const uint32_t* yr = y + row * PAIRS;
 #pragma unroll
@@ -441,7 +451,7 @@ __global__ void __launch_bounds__(256) k8_add_layernorm_kernel(const uint32_t* _
   const float rstd = rsqrtf(q / (2.0f * PAIRS) + eps);
 #pragma unroll
   for (int i = 0; i < PAIRS_PER_LANE; ++i) {
-    const float2 g = bf2_to_f2(gamma[lane + 32 * i]), b = bf2_to_f2(beta[lane + 32 * i]);
+    const float2 g = bf2_to_f2(HOIST ? gv[i] : gamma[lane + 32 * i]), b = bf2_to_f2(HOIST ? bv[i] : beta[lane + 32 * i]);
     __nv_bfloat162 o = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
     norm_out[row * PAIRS + lane + 32 * i] = *reinterpret_cast<uint32_t*>(&o);
   }
