@@ -526,13 +526,17 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
     }
-    if rank == 0 and world == 1 and not args.no_kernels and B == 1:
+    if world > 1:
+        dist.destroy_process_group()  # all collective work is done; rank 0 alone runs the kernel section
+    if rank == 0 and not args.no_kernels and B == 1:
+        # kernel rooflines: rank 0's GPU, after the timed region, at every N; the CPU baseline at N = 1 only
         kr = kernel_rooflines(dev, unet, peaks)
         line['roofline'] = kr['k3']
         line['roofline_k4'] = kr['k4']
         line['roofline_k2'] = kr['k2']
         line['roofline_k1'] = kr['k1']
         line['roofline_k5'] = kr['k5']
+    if rank == 0 and world == 1 and not args.no_kernels and B == 1:
         base, _ = cpu_reference_arm(2, 1)
         line['cpu_baseline'] = base
         cb = cpu_blend_baseline()
@@ -544,8 +548,6 @@ def main():
                                       '(BASELINE.json configs[0]); GPU batch 1024 prompts'}
     if rank == 0:
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
