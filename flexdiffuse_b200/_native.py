@@ -16,7 +16,7 @@ import torch
 LIB_NAME = 'libflexdiffuse_b200.so'
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
 
-FD_ABI_VERSION = 2
+FD_ABI_VERSION = 3
 FD_DTYPE_F32 = 0
 FD_DTYPE_BF16 = 1
 FD_BLEND_OK = 0
@@ -26,7 +26,7 @@ FD_BLEND_ZERO_DIVISION = 1
 ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_sm_count', 'fd_cfg_sched_step', 'fd_sim_blend',
                'fd_sim_blend_workspace_bytes',
-               'fd_kv_project', 'fd_cross_attn',
+               'fd_kv_project', 'fd_cross_attn', 'fd_cross_attn_fused',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
                'fd_composite_eps')
@@ -112,6 +112,11 @@ def lib() -> C.CDLL:
         C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp
     ]
     l.fd_cross_attn.restype = C.c_int
+    l.fd_cross_attn_fused.argtypes = [
+        vp, vp, vp, C.c_int64, C.c_int64, C.c_int, C.c_int, vp, vp, vp, C.c_int,
+        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, vp, vp, vp
+    ]
+    l.fd_cross_attn_fused.restype = C.c_int
     l.fd_groupnorm_act_workspace_bytes.argtypes = [C.c_int] * 4
     l.fd_groupnorm_act_workspace_bytes.restype = C.c_int64
     l.fd_add_bias_residual.argtypes = [vp, vp, vp, vp, C.c_int64, C.c_int, vp]
@@ -314,6 +319,48 @@ def cross_attn(q: torch.Tensor, kv: torch.Tensor, k_col_off: int,
     check(rc, 'fd_cross_attn')
     count_launch()
     return out
+
+
+# --------------------------------------------------------------------------- K3F
+def cross_attn_fused(x: torch.Tensor, wq: torch.Tensor, kv: torch.Tensor,
+                     k_col_off: int, v_col_off: int, ctx_index: torch.Tensor,
+                     wo: torch.Tensor, bo: torch.Tensor, heads: int, t_valid: int,
+                     t_pad: int, scale: float,
+                     attn: Optional[torch.Tensor] = None,
+                     out: Optional[torch.Tensor] = None):
+    '''fd_cross_attn_fused: x [S,Nq,C] bf16 -> (out, attn), both [S,Nq,C] bf16, where
+    attn = softmax(to_q(x) K^T scale) V over the K2 cache and out = to_out(attn) + bias.'''
+    _need(x, 'x', torch.bfloat16)
+    _need(wq, 'wq', torch.bfloat16)
+    _need(wo, 'wo', torch.bfloat16)
+    _need(bo, 'bo', torch.bfloat16)
+    _need(kv, 'kv', torch.bfloat16)
+    _need(ctx_index, 'ctx_index', torch.int32)
+    S, Nq, Cc = x.shape
+    if Cc % heads or tuple(wq.shape) != (Cc, Cc) or tuple(wo.shape) != (Cc, Cc) \
+            or bo.numel() != Cc:
+        raise NativeError('cross_attn_fused: weight shapes do not match x')
+    if attn is None:
+        attn = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    _need(attn, 'attn', torch.bfloat16)
+    _need(out, 'out', torch.bfloat16)
+    rc = lib().fd_cross_attn_fused(ptr(x), ptr(wq), ptr(kv), kv.shape[0], kv.shape[1],
+                                   k_col_off, v_col_off, ptr(ctx_index), ptr(wo),
+                                   ptr(bo), S, Nq, heads, Cc // heads, t_valid, t_pad,
+                                   float(scale), ptr(attn), ptr(out),
+                                   stream_ptr(x.device))
+    check(rc, 'fd_cross_attn_fused')
+    count_launch()
+    return out, attn
+
+
+def k3f_status(reset: bool = True):
+    '''Development aid: watchdog record of the fused kernel (all zeros = no wait timed out).'''
+    arr = (C.c_int * 4)()
+    check(lib().fd_debug_k3f_status(arr, int(reset)), 'fd_debug_k3f_status')
+    return list(arr)
 
 
 # --------------------------------------------------------------------------- K5 / K6

@@ -69,7 +69,11 @@ class CompositeGuide(GuideBase):
         return torch.cat([self.embed_tensor[:1], self.embed_tensor])
 
     def _ensure_cache(self):
+        key = (self.embed_tensor.data_ptr(), self.embed_tensor._version, self.guidance > 1.0)
+        if self._kv is not None and self.__dict__.get('_kv_key') != key:
+            self._kv = None
         if self._kv is None:
+            self._kv_key = key
             if not hasattr(self.unet, 'build_kv_cache'):
                 raise _native.NativeError('CompositeGuide needs flexdiffuse_b200.unet.'
                                           'UNet2DConditionModel (K2/K3 cross-attention)')

@@ -166,7 +166,8 @@ class FlexPipeline():
             if latents is not None:
                 if tuple(latents.shape) != shape:
                     raise ValueError(f'latents must be {shape}, got {tuple(latents.shape)}')
-                init_latents = latents.to(self.device, torch.float32)
+                # never write into the caller's tensor: it becomes a ping-pong buffer of the loop
+                init_latents = latents.to(self.device, torch.float32).clone()
             elif generator is not None and generator.device.type == 'cpu':
                 # host-side RNG (reproducible across devices): draw on the host, copy once
                 init_latents = torch.randn(shape, generator=generator).pin_memory().to(

@@ -55,9 +55,22 @@ class SimpleGuide(GuideBase):
     def classifier_free_guidance(self) -> bool:
         return self.guidance > 1.0  # guide.py:47
 
+    def _cache_key(self):
+        e, u = self.embeds, self.uncond_embeds
+        return (e.data_ptr(), e._version, tuple(e.shape), u.data_ptr(), u._version,
+                self.classifier_free_guidance)
+
+    def invalidate(self):
+        '''Forget the K/V cache (it is also rebuilt when `embeds`, `uncond_embeds` or the CFG
+        on/off state change: the reference reads these attributes on every step).'''
+        self._kv = None
+
     def _ensure_cache(self):
-        if self._kv is not None:
+        key = self._cache_key()
+        if self._kv is not None and self.__dict__.get('_kv_key') == key:
             return
+        self._kv_key = key
+        self.batch_size = self.embeds.shape[0]
         if not hasattr(self.unet, 'build_kv_cache'):
             raise _native.NativeError(
                 'SimpleGuide needs flexdiffuse_b200.unet.UNet2DConditionModel '
@@ -126,7 +139,9 @@ class SimpleGuide(GuideBase):
         modify `latents`.'''
         u, c = self.noise_pred_pair(latents, step)
         if u is None:
-            return c
+            # with CUDA graphs `c` is the runner's static output, overwritten by the next replay:
+            # a caller keeping a history of predictions must get its own tensor
+            return c.clone() if self.use_cuda_graph else c
         k = _native.SchedCoeffs()
         k.guidance, k.use_cfg = float(self.guidance), 1
         k.w[0], k.a, k.b = 1.0, 0.0, 1.0  # x' = eps : combine only

@@ -183,8 +183,11 @@ class DDIMScheduler(_SchedulerBase):
         def noise_fn(plan):
             if plan.c_noise == 0.0:
                 return None
-            return torch.randn(sample.shape, generator=generator,
-                               device=sample.device, dtype=torch.float32)
+            # diffusers 0.3.0 draws the eta noise on the host (`step` never sees the device);
+            # a CUDA generator draws in place, anything else on its own device then moves
+            gdev = generator.device if generator is not None else torch.device('cpu')
+            return torch.randn(sample.shape, generator=generator, device=gdev,
+                               dtype=torch.float32).to(sample.device)
 
         return self._run(self._plan(timestep, eta), eps_uncond, eps_cond,
                          guidance, use_cfg, sample, out, scaled_out, noise_fn)

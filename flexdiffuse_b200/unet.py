@@ -4,7 +4,8 @@ reference hands to `SimpleGuide`, /root/reference/pipeline/guide.py:9,56-58) wit
 
   * K2 `fd_kv_project`: to_k / to_v of the fixed 77-token context for ALL 16 layers in
     one tcgen05 GEMM, once per guide (`build_kv_cache`) instead of 32 Linears per step;
-  * K3 `fd_cross_attn`: softmax(Q K^T) V over that cache.
+  * K3F `fd_cross_attn_fused`: to_q, softmax(Q K^T) V over that cache and to_out (+ bias) in
+    one launch per site (K3 `fd_cross_attn` + two cuBLAS GEMMs when `FUSED_ATTN2` is off).
 
 Convolutions, GroupNorm, self-attention (SDPA) and the feed-forward stay in PyTorch
 (cuDNN / cuBLAS), as BASELINE.json's north_star prescribes.  Parameter names follow
@@ -136,7 +137,8 @@ class SelfAttention(nn.Module):
         self.to_q = nn.Linear(dim, dim, bias=False)
         self.to_k = nn.Linear(dim, dim, bias=False)
         self.to_v = nn.Linear(dim, dim, bias=False)
-        self.to_out = nn.Linear(dim, dim)
+        # diffusers 0.3.0: to_out = Sequential(Linear, Dropout) -> checkpoint keys `to_out.0.*`
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
 
     def _qkv_weight(self) -> torch.Tensor:
         '''to_q | to_k | to_v stacked into one [3C, C] matrix (one GEMM instead of three), cached
@@ -155,11 +157,16 @@ class SelfAttention(nn.Module):
         qkv = F.linear(x, self._qkv_weight()).view(B, N, 3, h, C // h)
         q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
         o = F.scaled_dot_product_attention(q, k, v)
-        return self.to_out(o.transpose(1, 2).reshape(B, N, C))
+        return self.to_out[0](o.transpose(1, 2).reshape(B, N, C))
+
+
+# attn2 runs as ONE launch of K3F (to_q + attention + to_out + bias).  False restores round 1's
+# cuBLAS to_q -> K3 -> cuBLAS to_out sequence (kept for A/B timing and as a second parity witness).
+FUSED_ATTN2 = True
 
 
 class CrossAttention(nn.Module):
-    '''attn2: to_q / to_out in cuBLAS, K/V from the K2 cache, attention in K3.'''
+    '''attn2: K/V from the K2 cache; to_q, attention and to_out in K3F (`fd_cross_attn_fused`).'''
     def __init__(self, dim: int, ctx_dim: int, heads: int):
         super().__init__()
         self.heads = heads
@@ -168,18 +175,26 @@ class CrossAttention(nn.Module):
         self.to_q = nn.Linear(dim, dim, bias=False)
         self.to_k = nn.Linear(ctx_dim, dim, bias=False)
         self.to_v = nn.Linear(ctx_dim, dim, bias=False)
-        self.to_out = nn.Linear(dim, dim)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
         self.k_col_off = -1  # set by UNet2DConditionModel.refresh_kv_weight
         self.v_col_off = -1
 
     def forward(self, x, kv: KVCache, ctx_index: torch.Tensor):
+        if FUSED_ATTN2 and self.dim % 320 == 0 and self.dim // self.heads in (40, 80, 160):
+            if not x.is_contiguous():
+                x = x.contiguous()
+            lin = self.to_out[0]
+            out, _ = _native.cross_attn_fused(x, self.to_q.weight, kv.kv, self.k_col_off,
+                                              self.v_col_off, ctx_index, lin.weight, lin.bias,
+                                              self.heads, T_VALID, T_PAD, self.scale)
+            return out
         q = self.to_q(x)
         if not q.is_contiguous():
             q = q.contiguous()
         o = _native.cross_attn(q, kv.kv, self.k_col_off, self.v_col_off,
                                ctx_index, self.heads, T_VALID, T_PAD,
                                self.scale)
-        return self.to_out(o)
+        return self.to_out[0](o)
 
 
 class GEGLU(nn.Module):
@@ -385,6 +400,7 @@ class UNet2DConditionModel(nn.Module):
         '''Pack every to_k / to_v weight into one [sum 2*C_l, 768] bf16 matrix (the B operand
         of K2) and record each layer's column offsets in the cache rows.'''
         rows, off = [], 0
+        self.__dict__['_derived_at'] = self._derived_key()
         for m in self.cross_attentions():
             m.k_col_off, m.v_col_off = off, off + m.dim
             rows += [m.to_k.weight, m.to_v.weight]
@@ -405,7 +421,9 @@ class UNet2DConditionModel(nn.Module):
     @torch.no_grad()
     def build_kv_cache(self, contexts: torch.Tensor) -> KVCache:
         '''contexts [n_ctx, 77, 768] (any float dtype) -> K/V of all 16 layers, one GEMM.'''
-        if self._kv_weight is None or self._kv_weight.device != contexts.device:
+        if self._kv_weight is None or self._kv_weight.device != contexts.device \
+                or self.__dict__.get('_derived_at') != self._derived_key():
+            self.invalidate_derived()
             self.refresh_kv_weight()
         n_ctx, t, d = contexts.shape
         if t != T_VALID:
@@ -416,10 +434,29 @@ class UNet2DConditionModel(nn.Module):
         kv = _native.kv_project(ctx.view(n_ctx * T_PAD, d), self._kv_weight)
         return KVCache(kv=kv, n_ctx=n_ctx)
 
+    def _derived_key(self):
+        '''(data_ptr, version) of every parameter the packed K/V and time-embedding weights are
+        built from: in-place edits and reloads both change it.'''
+        ps = []
+        for m in self.cross_attentions():
+            ps += [m.to_k.weight, m.to_v.weight]
+        for m in self.modules():
+            if isinstance(m, ResnetBlock2D):
+                ps += [m.time_emb_proj.weight, m.time_emb_proj.bias, m.conv1.bias]
+        return tuple((p.data_ptr(), p._version) for p in ps)
+
+    def invalidate_derived(self):
+        '''Drop everything computed from the parameters: packed weights and captured graphs
+        (a graph has the packed weights and its K/V buffer baked in by address).'''
+        self._kv_weight = None
+        self._tb_weight = None
+        for r in self.__dict__.get('_graph_runners', {}).values():
+            r.owner = None
+        self.__dict__['_graph_runners'] = {}
+
     def load_state_dict(self, *args, **kwargs):
         out = super().load_state_dict(*args, **kwargs)
-        self._kv_weight = None  # packed K/V and time-embedding weights are stale now
-        self._tb_weight = None
+        self.invalidate_derived()
         return out
 
     def set_attention_slice(self, slice_size):  # flex.py:102; memory knob only

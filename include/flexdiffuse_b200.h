@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 2
+#define FD_ABI_VERSION 3
 
 /* error codes */
 #define FD_OK            0
@@ -209,6 +209,30 @@ int fd_cross_attn(const void* q_bf16_dev,
                   float scale,                  /* d_head ** -0.5                           */
                   void* out_bf16_dev,
                   void* stream);
+
+/* ---- K3F: the whole attn2 layer in one launch ------------------------------------------ *
+ * Replaces diffusers' CrossAttention.forward for the 16 attn2 layers reached from
+ * pipeline/guide.py:56-58:   out = to_out( softmax( to_q(x) K^T * scale ) V ) + bias
+ * with K / V from the K2 cache (fd_kv_project), i.e. the to_q GEMM, the attention and the
+ * to_out GEMM (+ bias) that were three launches (cuBLAS, fd_cross_attn, cuBLAS) become one
+ * TMA-fed tcgen05 kernel: Q lives only in TMEM, the attention output crosses L2 once
+ * (`attn_bf16_dev`, also returned for inspection).  SURVEY 8d "fused variant": tensor-bound.
+ * x / attn / out are [n_samples, n_q, C] bf16 with C = heads*d_head a multiple of 320;
+ * wq / wo are the nn.Linear weights [C_out, C_in] row-major; bo the to_out bias [C].        */
+int fd_cross_attn_fused(const void* x_bf16_dev,       /* [n_samples, n_q, C] hidden states    */
+                        const void* wq_bf16_dev,      /* [C, C] to_q.weight                     */
+                        const void* kv_bf16_dev,      /* K2 output [n_ctx*t_pad, kv_row_stride] */
+                        int64_t kv_rows, int64_t kv_row_stride,
+                        int k_col_off, int v_col_off, /* element offsets, multiples of 8        */
+                        const int32_t* ctx_index_dev, /* [n_samples] context id of each sample  */
+                        const void* wo_bf16_dev,      /* [C, C] to_out[0].weight                */
+                        const void* bo_bf16_dev,      /* [C]    to_out[0].bias                  */
+                        int n_samples, int n_q, int heads, int d_head, /* d_head in {40,80,160} */
+                        int t_valid, int t_pad,       /* 77, 80                                 */
+                        float scale,                  /* d_head ** -0.5                         */
+                        void* attn_bf16_dev,          /* [n_samples, n_q, C] softmax(QK^T)V     */
+                        void* out_bf16_dev,           /* [n_samples, n_q, C] layer output       */
+                        void* stream);
 
 /* ---- K5 / K6: normalisation + activation glue of the UNet forward --------------------- *
  * The UNet call at pipeline/guide.py:56-58 spends ~45 % of a B=1 denoising step in ATen's

@@ -87,7 +87,7 @@ def attention(sd: SD, x, context):
                heads(_lin(sd, 'to_v', ctx)))
     scores = torch.einsum('bhid,bhjd->bhij', q, k) * d**-0.5
     o = torch.einsum('bhij,bhjd->bhid', scores.softmax(dim=-1), v)
-    return _lin(sd, 'to_out', o.permute(0, 2, 1, 3).reshape(B, N, C))
+    return _lin(sd, 'to_out.0', o.permute(0, 2, 1, 3).reshape(B, N, C))
 
 
 def transformer(sd: SD, x, context):

@@ -1,0 +1,125 @@
+'''Regressions for the round-1 advisor findings: checkpoint key names, caller-owned
+`latents`, stale derived weights / caches, DDIM eta > 0 with a host generator.'''
+import pytest
+import torch
+
+from flexdiffuse_b200 import schedulers as prod
+from flexdiffuse_b200.unet import UNet2DConditionModel
+
+
+def test_unet_state_dict_keys_match_diffusers_sd_v1():
+    '''diffusers 0.3.0 SD-v1 UNet: 686 tensors, attention output projection under `to_out.0.*`
+    (nn.Sequential(Linear, Dropout)), so `unet.load_state_dict(sd.unet.state_dict())` of
+    INTEGRATION.md works with strict loading.'''
+    with torch.device('meta'):
+        u = UNet2DConditionModel()
+    keys = list(u.state_dict().keys())
+    assert len(keys) == 686
+    assert sum(p.numel() for p in u.parameters()) == 859_520_964
+    to_out = [k for k in keys if '.to_out.' in k]
+    assert len(to_out) == 64 and all('.to_out.0.' in k for k in to_out)
+    for k in ('down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_out.0.bias',
+              'mid_block.attentions.0.transformer_blocks.0.attn1.to_out.0.weight',
+              'up_blocks.3.attentions.2.transformer_blocks.0.ff.net.0.proj.weight',
+              'time_embedding.linear_1.weight', 'conv_norm_out.weight'):
+        assert k in keys, k
+
+
+def test_oracle_unet_reads_the_same_keys():
+    '''The fp32 oracle consumes the product's state_dict unchanged (tiny config, CPU).'''
+    from oracle import unet_oracle as U
+    with torch.device('meta'):
+        u = UNet2DConditionModel()
+    sd = {k: torch.zeros(v.shape) for k, v in u.state_dict().items()
+          if k.startswith('mid_block.attentions.0.transformer_blocks.0.attn2.')}
+    sub = {k.split('attn2.')[1]: v for k, v in sd.items()}
+    out = U.attention(sub, torch.zeros(1, 4, 1280), torch.zeros(1, 77, 768))
+    assert tuple(out.shape) == (1, 4, 1280)
+
+
+class _Enc:
+    def __init__(self, uncond):
+        self.uncond = uncond
+
+    def prompt(self, p):
+        return self.uncond
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['DDIMScheduler', 'PNDMScheduler'])
+def test_caller_latents_are_not_overwritten(native, cuda_dev, name):
+    from flexdiffuse_b200.pipeline.flex import FlexPipeline
+    from flexdiffuse_b200.pipeline.guide import SimpleGuide
+    from tests.model_helpers import models
+    unet, vae, _, _ = models(str(cuda_dev))
+    g = torch.Generator(device=cuda_dev).manual_seed(3)
+    uncond = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    embeds = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    noise = torch.randn(1, 4, 16, 16, device=cuda_dev, generator=g)  # fp32, CUDA, contiguous
+    keep = noise.clone()
+    pipe = FlexPipeline(vae, None, None, unet, getattr(prod, name)())
+    outs = []
+    for _ in range(2):
+        # 4 steps: diffusers 0.3.0's PLMS indexes alphas_cumprod[t + 1], so (like the original) it
+        # only accepts step counts that divide the 1000 training steps
+        guide = SimpleGuide(_Enc(uncond), unet, 7.5, 4, embeds)
+        outs.append(pipe(guide, init_size=(128, 128), latents=noise, output_type='latent',
+                         return_dict=False).clone())
+        assert torch.equal(noise, keep)
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.gpu
+def test_ddim_eta_with_host_generator(native, cuda_dev):
+    from flexdiffuse_b200.pipeline.flex import FlexPipeline
+    from flexdiffuse_b200.pipeline.guide import SimpleGuide
+    from tests.model_helpers import models
+    unet, vae, _, _ = models(str(cuda_dev))
+    g = torch.Generator(device=cuda_dev).manual_seed(4)
+    uncond = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    embeds = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    pipe = FlexPipeline(vae, None, None, unet, prod.DDIMScheduler())
+    lats = []
+    for _ in range(2):
+        guide = SimpleGuide(_Enc(uncond), unet, 7.5, 3, embeds)
+        lats.append(pipe(guide, init_size=(128, 128), eta=0.7,
+                         generator=torch.Generator().manual_seed(11), output_type='latent',
+                         return_dict=False))
+    assert torch.isfinite(lats[0]).all()
+    assert torch.equal(lats[0], lats[1])
+
+
+@pytest.mark.gpu
+def test_guide_cache_follows_embeds_and_weights(native, cuda_dev):
+    '''Changing `guide.embeds`, flipping CFG, or reloading the UNet weights must not leave a stale
+    K/V cache or a stale captured graph behind.'''
+    from flexdiffuse_b200.pipeline.guide import SimpleGuide
+    from tests.model_helpers import models
+    unet, _, _, _ = models(str(cuda_dev))
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    uncond = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    e1 = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    e2 = torch.randn(1, 77, 768, device=cuda_dev, generator=g)
+    lat = torch.randn(1, 4, 16, 16, device=cuda_dev, generator=g)
+    guide = SimpleGuide(_Enc(uncond), unet, 7.5, 3, e1, use_cuda_graph=True)
+    a = guide.noise_pred(lat, 500).clone()
+    guide.embeds = e2
+    b = guide.noise_pred(lat, 500).clone()
+    fresh = SimpleGuide(_Enc(uncond), unet, 7.5, 3, e2, use_cuda_graph=False)
+    assert not torch.allclose(a, b)
+    torch.testing.assert_close(b, fresh.noise_pred(lat, 500), rtol=2e-2, atol=2e-2)
+    guide.guidance = 1.0  # CFG off: one sample per latent, cache rebuilt for the new layout
+    c = guide.noise_pred(lat, 500)
+    assert tuple(c.shape) == tuple(lat.shape) and torch.isfinite(c).all()
+    c2 = guide.noise_pred(lat, 400)
+    assert c.data_ptr() != c2.data_ptr()  # not the graph's static buffer
+    # reload (scaled) weights: packed K/V weights and graphs are rebuilt
+    guide.guidance = 7.5
+    sd = {k: v.clone() for k, v in unet.state_dict().items()}
+    try:
+        unet.load_state_dict({k: (v * 0.5 if 'attn2.to_v' in k else v) for k, v in sd.items()})
+        g2 = SimpleGuide(_Enc(uncond), unet, 7.5, 3, e2, use_cuda_graph=True)
+        d = g2.noise_pred(lat, 500)
+        assert not torch.allclose(b, d)
+    finally:
+        unet.load_state_dict(sd)

@@ -26,8 +26,12 @@ def fp32_math():
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
 
 
-def test_attn2_layers_match_oracle(native, cuda_dev, fp32_math):
-    '''Each of the 16 cross-attention sites: K2 cache + K3 vs fp32 to_k/to_v/softmax.'''
+@pytest.mark.parametrize('fused', [True, False])
+def test_attn2_layers_match_oracle(native, cuda_dev, fp32_math, fused, monkeypatch):
+    '''Each of the 16 cross-attention sites: K2 cache + K3F (one launch: to_q, attention, to_out)
+    -- or K3 between two cuBLAS GEMMs -- vs fp32 to_q/to_k/to_v/softmax/to_out.'''
+    from flexdiffuse_b200 import unet as unet_mod
+    monkeypatch.setattr(unet_mod, 'FUSED_ATTN2', fused)
     unet, _, sd, _ = models(str(cuda_dev))
     g = torch.Generator(device=cuda_dev).manual_seed(3)
     ctx = torch.randn(3, 77, 768, device=cuda_dev, generator=g)
@@ -38,7 +42,10 @@ def test_attn2_layers_match_oracle(native, cuda_dev, fp32_math):
     for name, mod in zip(names, unet.cross_attentions()):
         n_q = {320: 1024, 640: 256, 1280: 64}[mod.dim]
         x = torch.randn(4, n_q, mod.dim, device=cuda_dev, generator=g)
+        before = native.LAUNCHES
         got = mod(x.bfloat16(), kv, idx)
+        assert native.LAUNCHES - before == 1  # K3F or K3: one native launch either way
+        assert native.k3f_status() == [0, 0, 0, 0]
         want = U.attention(U._sub(sd, name + '.'), x.bfloat16().float(),
                            ctx.bfloat16().float()[idx.long()])
         assert rel_l2(got, want) < ATTN_TOL, name
