@@ -327,9 +327,12 @@ def cross_attn_fused(x: torch.Tensor, wq: torch.Tensor, kv: torch.Tensor,
                      wo: torch.Tensor, bo: torch.Tensor, heads: int, t_valid: int,
                      t_pad: int, scale: float,
                      attn: Optional[torch.Tensor] = None,
-                     out: Optional[torch.Tensor] = None):
+                     out: Optional[torch.Tensor] = None,
+                     want_attn: bool = True):
     '''fd_cross_attn_fused: x [S,Nq,C] bf16 -> (out, attn), both [S,Nq,C] bf16, where
-    attn = softmax(to_q(x) K^T scale) V over the K2 cache and out = to_out(attn) + bias.'''
+    attn = softmax(to_q(x) K^T scale) V over the K2 cache and out = to_out(attn) + bias.
+    `want_attn=False` with C == 320 keeps the attention output on chip (attn is None); wider
+    layers always need the buffer (their head groups exchange it through L2).'''
     _need(x, 'x', torch.bfloat16)
     _need(wq, 'wq', torch.bfloat16)
     _need(wo, 'wo', torch.bfloat16)
@@ -340,11 +343,12 @@ def cross_attn_fused(x: torch.Tensor, wq: torch.Tensor, kv: torch.Tensor,
     if Cc % heads or tuple(wq.shape) != (Cc, Cc) or tuple(wo.shape) != (Cc, Cc) \
             or bo.numel() != Cc:
         raise NativeError('cross_attn_fused: weight shapes do not match x')
-    if attn is None:
+    if attn is None and (want_attn or Cc != 320):
         attn = torch.empty_like(x)
     if out is None:
         out = torch.empty_like(x)
-    _need(attn, 'attn', torch.bfloat16)
+    if attn is not None:
+        _need(attn, 'attn', torch.bfloat16)
     _need(out, 'out', torch.bfloat16)
     rc = lib().fd_cross_attn_fused(ptr(x), ptr(wq), ptr(kv), kv.shape[0], kv.shape[1],
                                    k_col_off, v_col_off, ptr(ctx_index), ptr(wo),

@@ -8,24 +8,31 @@
 //   guidance.py:215-272  Tweener.tween
 // Algorithm spec: SURVEY.md 3.6 (verified bit-level against the reference by the oracle tests).
 //
-// A tiny prep kernel splits the (usually shared) guide once into tf32 hi / lo planes and its inverse
-// L2 norms.  Structure of one CTA of the main kernel (384 threads, 1 CTA / SM):
-//   1. GEMM  D[i,j] = <guide_i, text_j>  (A<=384 x T<=80 x D) on tcgen05, kind::tf32 with the
-//      3-pass hi/lo split (hi*hi + lo*hi + hi*lo) so the logits are fp32-equivalent
-//      (a single bf16/tf32 pass flips arg-max / threshold decisions).
-//      Warp-specialised 2-stage pipeline over K chunks of 32: warp 0 TMA-loads the guide hi / lo
-//      tiles (SWIZZLE_128B), warps 2-11 split the prompt's own chunk in registers into the same
-//      layout (+ sum of squares for its L2 norms), warp 1 issues the MMAs.  Guide rows beyond the
-//      last full 128-row tile (the 257th CLIP token) are <= 8 dot products per text token and go
-//      to the CUDA cores instead of wasting a third MMA tile.
+// A tiny prep kernel L2-normalises the (usually shared) guide once and splits it into two fp16
+// planes.  Structure of one CTA of the main kernel (256 threads, two CTAs per SM so one prompt's
+// softmax / mapping / blend tail overlaps the other's GEMM):
+//   1. GEMM  D[j,i] = <text_j, guide_i>  (T<=80 x A<=384 x D) on tcgen05 kind::f16 with a TWO-TERM
+//      fp16 split of both operands, x * 2^k = h1 + h2 with h1 = fp16(x 2^k), h2 = fp16(x 2^k - h1):
+//      11 + 11 mantissa bits, so h2.h1 + h1.h2 + h1.h1 (exact products, fp32 accumulation) carries
+//      the logits to fp32 accuracy -- a single bf16 / tf32 pass flips arg-max / threshold
+//      decisions.  Round 1 used three tf32 products (hi/lo, K = 8 per MMA): the fp16
+//      split issues half the MMAs (K = 16) and moves half the operand bytes for the same accuracy.
+//      The powers of two (2^6 for the raw text rows, 2^12 for the unit-norm guide rows) keep h2
+//      out of the fp16 subnormals; they are exact and divided out with the norms.  |text| >= 1023
+//      would overflow fp16: such a prompt is flagged FD_BLEND_RANGE instead of being blended.
+//      Warp-specialised over K chunks of 64: warp 0 TMA-loads the guide planes (SWIZZLE_128B),
+//      warps 2-7 split the prompt's own chunk in registers into the same layout (+ sum of squares
+//      for its L2 norms), warp 1 issues the MMAs.  Guide rows beyond the last multiple of 16 (the
+//      257th CLIP token) are <= 8 dot products per text token and go to the CUDA cores in exact fp32.
 //      Accumulator: 128 lanes (text tokens) x up to 384 columns (guide tokens) in TMEM.
-//      (Tried and measured slower on B200, see git history / profiles/r01/SUMMARY.md: a 6-product
-//      bf16 hi/mid/lo split with SWIZZLE_64B or SWIZZLE_32B chunks and up to 5 stages.)
+//      (Tried and measured slower on B200, see profiles/r01/SUMMARY.md: a 6-product bf16
+//      hi/mid/lo split with SWIZZLE_64B or SWIZZLE_32B chunks and up to 5 stages.)
 //   2. Softmax over the text tokens: one thread per TMEM lane (= guide token), no shuffles.
 //      P^T is parked in shared memory (aliasing the operand staging area).
 //   3. Column arg-max / greedy no-reuse assignment / direct mapping: warp-shuffle reductions.
 //   4. Weight heuristics for <=96 tokens in one warp (ballot bitmasks for peaks / valleys).
 //   5. 3-way select / lerp of the [T, D] rows, 128-bit coalesced.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include "fd_common.cuh"
@@ -38,7 +45,9 @@ constexpr int K1_THREADS = 256;   // 128 registers x 256 threads: two CTAs per S
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int NPAD = 80;          // UMMA N (text tokens padded)
 constexpr int MAX_TILES = 3;      // guide tokens padded to <= 3 x 128
-constexpr int KC = 32;            // fp32 per K chunk (one 128 B swizzle row)
+constexpr int KC = 64;            // elements per K chunk (64 fp16 = one 128 B swizzle row)
+constexpr float TEXT_SCALE = 64.0f;     // 2^6: raw text rows (|x| < 1023)
+constexpr float GUIDE_SCALE = 4096.0f;  // 2^12: unit-norm guide rows
 constexpr int TXT_TILE_BYTES = 128 * 128;  // M operand: 128 rows (80 used) x 128 B, hi and lo
 constexpr int MAX_A = MAX_TILES * 128;     // 384 guide tokens
 constexpr int MAX_REM = 8;        // guide rows past the last multiple of 16 that go to the CUDA cores
@@ -46,7 +55,7 @@ constexpr int TEXT_WARPS = K1_WARPS - 2;
 constexpr int TEXT_THREADS = TEXT_WARPS * 32;                                // 192
 constexpr int PT_STRIDE_MAX = MAX_A + 1;   // floats per P^T row: A | 1 (odd => conflict-free row-per-lane stores)
 constexpr int MAXT = 80;
-constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 4
+constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 4 items of 8 elements per thread and chunk
 
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
@@ -94,7 +103,7 @@ struct K1Smem {
   int sel[MAXT + 16];
   float slerp_a[MAXT + 16], slerp_b[MAXT + 16];  // FD_BLEND_MODE_SLERP row coefficients
   float rem[MAX_REM][NPAD];  // raw dot products of the remainder guide rows
-  int pick_r, pick_i, flag;
+  int pick_r, pick_i, flag, range_flag;
   uint64_t full_bar[2], empty_bar[2], done_bar;
   uint32_t tmem_slot;
 };
@@ -153,32 +162,41 @@ __device__ __forceinline__ int warp_consume_all_unused(unsigned int* used, int A
   return hi;
 }
 
-// guide fp32 -> tf32 hi plane, lo plane (x - hi, exact in fp32) and 1 / |row|.  One warp per row.
-__global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, float* __restrict__ hi,
-                                                            float* __restrict__ lo, float* __restrict__ inv_norm,
+// guide fp32 -> 1 / |row|, and the two fp16 planes of (row / |row|) * 2^12 (normalise first, then
+// multiply, as the reference does: guidance.py:43-44).  One warp per row, the row stays in L1.
+__global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, __half* __restrict__ h1p,
+                                                            __half* __restrict__ h2p, float* __restrict__ inv_norm,
                                                             int rows, int D) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
+  const float* src = g + static_cast<size_t>(row) * D;
   float ss = 0.f;
   for (int c = lane * 4; c < D; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(g + static_cast<size_t>(row) * D + c);
-    float4 h, l;
-    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-    l.x = v.x - h.x;
-    l.y = v.y - h.y;
-    l.z = v.z - h.z;
-    l.w = v.w - h.w;
-    *reinterpret_cast<float4*>(hi + static_cast<size_t>(row) * D + c) = h;
-    *reinterpret_cast<float4*>(lo + static_cast<size_t>(row) * D + c) = l;
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
     ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if (lane == 0) inv_norm[row] = 1.0f / sqrtf(ss);
+  const float nrm = sqrtf(ss);
+  if (lane == 0) inv_norm[row] = 1.0f / nrm;
+  for (int c = lane * 4; c < D; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(src + c);
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __half a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float xs = nrm > 0.f ? __fdiv_rn(x[k], nrm) * GUIDE_SCALE : 0.f;
+      a[k] = __float2half_rn(xs);
+      b[k] = __float2half_rn(xs - __half2float(a[k]));
+    }
+    *reinterpret_cast<uint2*>(h1p + static_cast<size_t>(row) * D + c) =
+        make_uint2(static_cast<uint32_t>(__half_as_ushort(a[0])) | (static_cast<uint32_t>(__half_as_ushort(a[1])) << 16),
+                   static_cast<uint32_t>(__half_as_ushort(a[2])) | (static_cast<uint32_t>(__half_as_ushort(a[3])) << 16));
+    *reinterpret_cast<uint2*>(h2p + static_cast<size_t>(row) * D + c) =
+        make_uint2(static_cast<uint32_t>(__half_as_ushort(b[0])) | (static_cast<uint32_t>(__half_as_ushort(b[1])) << 16),
+                   static_cast<uint32_t>(__half_as_ushort(b[2])) | (static_cast<uint32_t>(__half_as_ushort(b[3])) << 16));
+  }
 }
 
 __global__ void __launch_bounds__(K1_THREADS, 2)
@@ -215,6 +233,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       mbar_init(&sm.empty_bar[st], 1);
     }
     mbar_init(&sm.done_bar, 1);
+    sm.range_flag = 0;
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -251,10 +270,10 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: D[text j, guide i] += text(128 x 8) . guide(N x 8)^T, three tf32 products
+    // ---- MMA issuer: D[text j, guide i] += text(128 x 16) . guide(N x 16)^T, three fp16 products
     if (elect_one()) {
-      const uint32_t idesc0 = umma_idesc(UMMA_TF32, 128, n_blk0, 0, 0);
-      const uint32_t idesc1 = umma_idesc(UMMA_TF32, 128, n_blk1 > 0 ? n_blk1 : 16, 0, 0);
+      const uint32_t idesc0 = umma_idesc(UMMA_F16, 128, n_blk0, 0, 0);
+      const uint32_t idesc1 = umma_idesc(UMMA_F16, 128, n_blk1 > 0 ? n_blk1 : 16, 0, 0);
       for (int kc = 0; kc < num_kc; ++kc) {
         const int st = kc % nst;
         mbar_wait_backoff(&sm.full_bar[st], (kc / nst) & 1);
@@ -265,18 +284,18 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
         const uint64_t gh = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES), 16, 1024);
         const uint64_t gl = umma_desc_sw128(smem_u32(base + 2 * TXT_TILE_BYTES + g_plane), 16, 1024);
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {  // UMMA_K = 8 for tf32 = 32 B = +2 in the desc
-          mma_tf32_ss(tmem_base, tl + 2 * ks, gh + 2 * ks, idesc0, (kc | ks) != 0);  // small terms first
-          mma_tf32_ss(tmem_base, th + 2 * ks, gl + 2 * ks, idesc0, 1);
-          mma_tf32_ss(tmem_base, th + 2 * ks, gh + 2 * ks, idesc0, 1);
+        for (int ks = 0; ks < KC / 16; ++ks) {  // UMMA_K = 16 for fp16 = 32 B = +2 in the desc
+          mma_f16_ss(tmem_base, tl + 2 * ks, gh + 2 * ks, idesc0, (kc | ks) != 0);  // small terms first
+          mma_f16_ss(tmem_base, th + 2 * ks, gl + 2 * ks, idesc0, 1);
+          mma_f16_ss(tmem_base, th + 2 * ks, gh + 2 * ks, idesc0, 1);
         }
         if (n_blk1 > 0) {
           const uint64_t gh2 = gh + ((256 * 128) >> 4), gl2 = gl + ((256 * 128) >> 4);
 #pragma unroll
-          for (int ks = 0; ks < KC / 8; ++ks) {
-            mma_tf32_ss(tmem_base + 256, tl + 2 * ks, gh2 + 2 * ks, idesc1, (kc | ks) != 0);
-            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gl2 + 2 * ks, idesc1, 1);
-            mma_tf32_ss(tmem_base + 256, th + 2 * ks, gh2 + 2 * ks, idesc1, 1);
+          for (int ks = 0; ks < KC / 16; ++ks) {
+            mma_f16_ss(tmem_base + 256, tl + 2 * ks, gh2 + 2 * ks, idesc1, (kc | ks) != 0);
+            mma_f16_ss(tmem_base + 256, th + 2 * ks, gl2 + 2 * ks, idesc1, 1);
+            mma_f16_ss(tmem_base + 256, th + 2 * ks, gh2 + 2 * ks, idesc1, 1);
           }
         }
         tc_commit(&sm.empty_bar[st]);
@@ -284,33 +303,42 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       tc_commit(&sm.done_bar);
     }
   } else {
-    // ---- text warps: this prompt's chunk -> registers -> hi / lo split -> swizzled smem
+    // ---- text warps: this prompt's chunk -> registers -> fp16 h1 / h2 split -> swizzled smem.
+    // An item is 8 consecutive elements of one row (two float4 loads in, one 16-byte store per plane
+    // out); the 8 threads that share a row sit in one aligned group of 8 lanes.
     const int tt = tid - 64;
-    float4 rb[B_ITEMS];
+    float4 rb[B_ITEMS][2];
     float ssb[B_ITEMS];
 #pragma unroll
     for (int j = 0; j < B_ITEMS; ++j) ssb[j] = 0.f;
     // A single remainder guide row (A = 257: the usual case) is folded into this loop: the thread
-    // already holds 4 consecutive floats of its text rows for every chunk, so the exact-fp32 dot
-    // product with the row's matching 4 floats costs one cached load + 4 FMAs per item instead of a
-    // separate, latency-bound pass after the GEMM feed (it was ~16 us of a 78 us CTA).
+    // already holds 8 consecutive floats of its text rows for every chunk, so the exact-fp32 dot
+    // product with the row's matching 8 floats costs two cached loads + 8 FMAs per item instead of a
+    // separate, latency-bound pass after the GEMM feed.
     const int n_rem = A - a.a_mma;
     const bool fold_rem = n_rem == 1;
-    const float* grem = a.guide + (static_cast<size_t>(g_idx) * A + a.a_mma) * D + (tt & 7) * 4;
-    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* grem = a.guide + (static_cast<size_t>(g_idx) * A + a.a_mma) * D + (tt & 7) * 8;
+    float4 gq0 = make_float4(0.f, 0.f, 0.f, 0.f), gq1 = gq0;
     float racc[B_ITEMS];
+    bool out_of_range = false;
 #pragma unroll
     for (int j = 0; j < B_ITEMS; ++j) racc[j] = 0.f;
-    static_assert(TEXT_THREADS % 8 == 0, "all items of a thread share the same 4-float column slice");
+    static_assert(TEXT_THREADS % 8 == 0, "all items of a thread share the same 8-element column slice");
     auto load_chunk = [&](int kc) {
-      if (fold_rem) gq = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
+      if (fold_rem) {
+        gq0 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
+        gq1 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC) + 1);
+      }
 #pragma unroll
       for (int j = 0; j < B_ITEMS; ++j) {
         const int f = tt + j * TEXT_THREADS;
-        if (f < T * 8)
-          rb[j] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + (f & 7));
-        else
-          rb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < T * 8) {
+          const float4* src = reinterpret_cast<const float4*>(text + static_cast<size_t>(f >> 3) * D + kc * KC) + 2 * (f & 7);
+          rb[j][0] = __ldg(src);
+          rb[j][1] = __ldg(src + 1);
+        } else {
+          rb[j][0] = rb[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     };
     load_chunk(0);
@@ -323,21 +351,30 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       for (int j = 0; j < B_ITEMS; ++j) {
         const int f = tt + j * TEXT_THREADS;
         if (f < NPAD * 8) {  // rows T..79 are written as zeros; rows 80..127 feed ignored TMEM lanes
-          const float4 v = rb[j];
+          const float x[8] = {rb[j][0].x, rb[j][0].y, rb[j][0].z, rb[j][0].w,
+                              rb[j][1].x, rb[j][1].y, rb[j][1].z, rb[j][1].w};
+          uint32_t ph[4], pl[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x0 = x[2 * q] * TEXT_SCALE, x1 = x[2 * q + 1] * TEXT_SCALE;
+            out_of_range |= !(fabsf(x0) < 65504.f) | !(fabsf(x1) < 65504.f);
+            const __half a0 = __float2half_rn(x0), a1 = __float2half_rn(x1);
+            const __half b0 = __float2half_rn(x0 - __half2float(a0)), b1 = __float2half_rn(x1 - __half2float(a1));
+            ph[q] = static_cast<uint32_t>(__half_as_ushort(a0)) | (static_cast<uint32_t>(__half_as_ushort(a1)) << 16);
+            pl[q] = static_cast<uint32_t>(__half_as_ushort(b0)) | (static_cast<uint32_t>(__half_as_ushort(b1)) << 16);
+          }
           const uint32_t off = sw128_offset(f >> 3, f & 7);
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          l.x = v.x - h.x;
-          l.y = v.y - h.y;
-          l.z = v.z - h.z;
-          l.w = v.w - h.w;
-          *reinterpret_cast<float4*>(t_hi + off) = h;
-          *reinterpret_cast<float4*>(t_lo + off) = l;
-          ssb[j] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-          racc[j] = fmaf(v.x, gq.x, fmaf(v.y, gq.y, fmaf(v.z, gq.z, fmaf(v.w, gq.w, racc[j]))));
+          *reinterpret_cast<uint4*>(t_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(t_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          float ss = ssb[j], ra = racc[j];
+          const float gq[8] = {gq0.x, gq0.y, gq0.z, gq0.w, gq1.x, gq1.y, gq1.z, gq1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ss += x[q] * x[q];
+            ra = fmaf(x[q], gq[q], ra);
+          }
+          ssb[j] = ss;
+          racc[j] = ra;
         }
       }
       fence_proxy_async_smem();
@@ -345,6 +382,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       if (lane == 0) mbar_arrive(&sm.full_bar[st]);
       if (kc + 1 < num_kc) load_chunk(kc + 1);  // in flight while the MMAs of this chunk run
     }
+    if (out_of_range) sm.range_flag = 1;
     // L2 norms of the text rows: the 8 threads that share a row sit in one aligned group of 8 lanes
 #pragma unroll
     for (int j = 0; j < B_ITEMS; ++j) {
@@ -406,7 +444,8 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     {
       const int quarter = warp & 3, third = warp >> 2;  // K1_WARPS / 4 warps share a TMEM lane quarter
       const int j = quarter * 32 + lane;
-      const float sb = (j < T) ? sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f) : 0.f;
+      // the guide planes are unit rows x 2^12, the text planes raw rows x 2^6: both scales are exact
+      const float sb = (j < T) ? sm.inv_norm_b[j] * (100.0f * 1.4426950408889634f / (TEXT_SCALE * GUIDE_SCALE)) : 0.f;
       for (int c0 = third * 32; c0 < a.a_mma; c0 += (K1_WARPS / 4) * 32) {
         uint32_t v[2][16];
 #pragma unroll
@@ -419,7 +458,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               const int i = c0 + 16 * g + q;
-              if (i < a.a_mma) pt_full[j * PT_STRIDE + i] = __uint_as_float(v[g][q]) * sb * sm.inv_norm_a[i];
+              if (i < a.a_mma) pt_full[j * PT_STRIDE + i] = __uint_as_float(v[g][q]) * sb;
             }
         }
       }

@@ -48,6 +48,7 @@ constexpr int F_TAIL = 2048;              // barriers + TMEM slot + bias
 constexpr int F_SMEM = 1024 + F_ARENA + F_TAIL;
 constexpr int F_TMEM_COLS = 512;
 constexpr int F_S_BASE = 320;
+constexpr int F_ACC_BASE = 192;            // to_out accumulator: TMEM [192, 512)
 static_assert(F_SMEM <= 227 * 1024, "K3F shared memory");
 
 template <int DH>
@@ -81,7 +82,7 @@ __device__ long long g_k3f_trace[64];
 struct FArgs {
   const int32_t* ctx_index;
   const __nv_bfloat16* bias;
-  int n_q, t_valid, t_pad, kchunks, G, phases, trace;
+  int n_q, t_valid, t_pad, kchunks, G, phases, trace, store_attn;
   float scale_log2e;
 };
 
@@ -149,8 +150,30 @@ __device__ __forceinline__ void remote_mbar_arrive(uint64_t* bar, uint32_t cta_r
 enum : int {
   W_EMPTY = 1, W_FULL = 2, W_QDONE_P = 3, W_QDONE_W = 4, W_KV = 5, W_QC = 6, W_SFULL = 7, W_PFULL = 8,
   W_OFULL = 9, W_OFREE = 10, W_OSTFULL = 11, W_OSTFREE = 12, W_OREADY = 13, W_OUTFULL = 14,
-  W_EMPTY5 = 15, W_FULL5 = 16
+  W_EMPTY5 = 15, W_FULL5 = 16, W_OBF = 17
 };
+
+// P6 helper: NG 16-column groups of the fp32 accumulator (from group c_first) + bias -> bf16 -> the
+// SWIZZLE_128B staging chunks at the head of the arena (one TMEM round trip for the NG groups)
+template <int NG>
+__device__ __forceinline__ void p6_groups(uint32_t tacc, int c_first, const float* bias_s, uint8_t* arena, int row) {
+  uint32_t v[NG][16];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) tmem_ld_x16(tacc + 16 * (c_first + q), v[q]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int q = 0; q < NG; ++q) {
+    const int c = c_first + q;
+    uint32_t pk[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      pk[k] = pack_bf16x2(__uint_as_float(v[q][2 * k]) + bias_s[16 * c + 2 * k],
+                          __uint_as_float(v[q][2 * k + 1]) + bias_s[16 * c + 2 * k + 1]);
+    uint8_t* chunk = arena + (c >> 2) * F_Q_CHUNK;
+    *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3) + 1)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+}
 
 template <int DH>
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -170,8 +193,9 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint64_t* full = bars;                 // [4]
   uint64_t* empty = full + F_STAGES;     // [4]
   uint64_t* q_done = empty + F_STAGES;   // Q accumulator complete
-  uint64_t* kv_full = q_done + 1;
-  uint64_t* qc_done = kv_full + 1;       // bf16 Q in place (8 warps)
+  uint64_t* k_full = q_done + 1;         // [8] K tile of head j landed
+  uint64_t* v_full = k_full + 8;         // [8] V tile of head j landed
+  uint64_t* qc_done = v_full + 8;        // bf16 Q in place (8 warps)
   uint64_t* s_full = qc_done + 1;        // [2]
   uint64_t* p_full = s_full + 2;         // [2] (4 warps)
   uint64_t* o_full = p_full + 2;         // [2]
@@ -180,7 +204,8 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint64_t* ost_free = ost_full + 2;     // [2] (producer)
   uint64_t* o_ready = ost_free + 2;      // every CTA of the cluster has stored its heads (G arrivals)
   uint64_t* out_full = o_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_full + 1);
+  uint64_t* obf_done = out_full + 1;     // every head's bf16 output is in TMEM (8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(obf_done + 1);
   volatile int* abort_s = reinterpret_cast<volatile int*>(tmem_slot + 1);
   float* bias_s = reinterpret_cast<float*>(arena + F_ARENA + 512);   // [320]
 
@@ -206,7 +231,10 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       mbar_init(&empty[s], 1);
     }
     mbar_init(q_done, 1);
-    mbar_init(kv_full, 1);
+    for (int j = 0; j < 8; ++j) {
+      mbar_init(&k_full[j], 1);
+      mbar_init(&v_full[j], 1);
+    }
     mbar_init(qc_done, 8);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
@@ -218,9 +246,19 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     }
     mbar_init(o_ready, static_cast<uint32_t>(a.G));
     mbar_init(out_full, 1);
+    mbar_init(obf_done, 8);
     *abort_s = 0;
     fence_mbar_init();
     fence_proxy_async_smem();
+    // the first F_STAGES k-chunks of P1 go out now, under the TMEM allocation and the CTA barrier
+    // (their barriers were initialised by this very thread; nothing else touches the ring yet)
+    for (int kc = 0; kc < F_STAGES && kc < KC; ++kc) {
+      uint8_t* st = arena + kc * F_STAGE_BYTES;
+      mbar_expect_tx(&full[kc], F_STAGE_BYTES);
+      tma_load_3d(st, &tm_x, &full[kc], kc * 64, row0, sample);
+      tma_load_2d(st + F_A_BYTES, &tm_wq, &full[kc], kc * 64, g * F_NQ);
+      tma_load_2d(st + F_A_BYTES + F_NB * 128, &tm_wq, &full[kc], kc * 64, g * F_NQ + F_NB);
+    }
   }
   if (threadIdx.x >= 64) {  // this group's to_out bias as fp32
     const int i = threadIdx.x - 64;
@@ -244,6 +282,7 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       int it = 0;
       auto gemm_loads = [&](const CUtensorMap* ta, const CUtensorMap* tb, int wcode) {
         for (int kc = 0; kc < KC; ++kc, ++it) {
+          if (it < F_STAGES) continue;  // issued before the CTA barrier
           const int s = it % F_STAGES;
           wd_wait(&empty[s], ((it / F_STAGES) & 1) ^ 1, wcode, abort_s);
           uint8_t* st = arena + s * F_STAGE_BYTES;
@@ -259,44 +298,67 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         // ---- K / V of this group's heads: the ring is dead once the Q accumulator is complete
         wd_wait(q_done, 0, W_QDONE_P, abort_s);
         const int ctx_row = __ldg(a.ctx_index + sample) * a.t_pad;
-        mbar_expect_tx(kv_full, Cfg::KV_BYTES);
+        // one barrier per tile, in the order the MMA thread needs them (K_0, V_0, K_1, ...): the
+        // first head starts as soon as ITS 2 x NCHUNK x 10 KB are in, the rest lands under the softmax
 #pragma unroll 1
         for (int j = 0; j < HG; ++j) {
           uint8_t* kj = kv_s + j * Cfg::KV_HEAD_BYTES;
           uint8_t* vj = kj + Cfg::NCHUNK * F_KV_CHUNK;
-#pragma unroll
-          for (int c = 0; c < Cfg::NCHUNK; ++c) {
-            tma_load_3d(kj + c * F_KV_CHUNK, &tm_k, kv_full, c * 64, g * HG + j, ctx_row);
-            tma_load_3d(vj + c * F_KV_CHUNK, &tm_v, kv_full, c * 64, g * HG + j, ctx_row);
-          }
-        }
-        // ---- P3: ship each head's output tile as its warpgroup stages it
-#pragma unroll 1
-        for (int j = 0; j < HG; ++j) {
-          const int w = j & 1;
-          wd_wait(&ost_full[w], (j >> 1) & 1, W_OSTFULL, abort_s);
+          mbar_expect_tx(&k_full[j], Cfg::NCHUNK * F_KV_CHUNK);
 #pragma unroll
           for (int c = 0; c < Cfg::NCHUNK; ++c)
-            tma_store_4d(&tm_os, ost_s + w * Cfg::OST_BYTES + c * F_Q_CHUNK, c * 64, g * HG + j, row0, sample);
-          tma_store_commit();
-          tma_store_wait_read<0>();
-          mbar_arrive(&ost_free[w]);
+            tma_load_3d(kj + c * F_KV_CHUNK, &tm_k, &k_full[j], c * 64, g * HG + j, ctx_row);
+          mbar_expect_tx(&v_full[j], Cfg::NCHUNK * F_KV_CHUNK);
+#pragma unroll
+          for (int c = 0; c < Cfg::NCHUNK; ++c)
+            tma_load_3d(vj + c * F_KV_CHUNK, &tm_v, &v_full[j], c * 64, g * HG + j, ctx_row);
         }
-        tma_store_wait_all();  // writes performed, not just read
-        fence_proxy_async_all();
+        // ---- P3: ship each head's output tile as its warpgroup stages it (only when somebody reads
+        // it from global memory: the other head groups of the cluster, or the caller)
+        if (a.store_attn) {
+#pragma unroll 1
+          for (int j = 0; j < HG; ++j) {
+            const int w = j & 1;
+            wd_wait(&ost_full[w], (j >> 1) & 1, W_OSTFULL, abort_s);
+#pragma unroll
+            for (int c = 0; c < Cfg::NCHUNK; ++c)
+              tma_store_4d(&tm_os, ost_s + w * Cfg::OST_BYTES + c * F_Q_CHUNK, c * 64, g * HG + j, row0, sample);
+            tma_store_commit();
+            tma_store_wait_read<0>();
+            mbar_arrive(&ost_free[w]);
+          }
+          tma_store_wait_all();  // writes performed, not just read
+          fence_proxy_async_all();
+        }
         F_STAMP(48);
       }
       if (a.phases & 4) {
-        // ---- P4: all head groups of this query tile are in global memory
+        // ---- P4 / P5.  Chunk order: this group's own 5 k-chunks first -- their A operand is the bf16
+        // attention output sitting in TMEM, so only Wo travels -- then the other groups' chunks,
+        // whose A operand comes back from global memory once the whole cluster has stored its heads.
+        const bool own_tmem = (a.phases & 2) != 0;
         if (a.G > 1) {
           __threadfence();
           for (int p = 0; p < a.G; ++p) remote_mbar_arrive(o_ready, static_cast<uint32_t>(p));
-          wd_wait<true>(o_ready, 0, W_OREADY, abort_s);
-          fence_proxy_async_all();
         }
-        F_STAMP(49);
-        // ---- P5
-        gemm_loads(&tm_oa, &tm_wo, W_EMPTY5);
+        if (own_tmem) wd_wait(obf_done, 0, W_OBF, abort_s);  // K / V and staging are dead: the ring may refill
+        for (int i = 0; i < KC; ++i, ++it) {
+          const int o = i - 5;
+          const int kc = i < 5 ? g * 5 + i : (o < g * 5 ? o : o + 5);
+          const bool a_from_tmem = own_tmem && i < 5;
+          if (i == 5) {
+            wd_wait<true>(o_ready, 0, W_OREADY, abort_s);
+            fence_proxy_async_all();
+            F_STAMP(49);
+          }
+          const int s = it % F_STAGES;
+          wd_wait(&empty[s], ((it / F_STAGES) & 1) ^ 1, W_EMPTY5, abort_s);
+          uint8_t* st = arena + s * F_STAGE_BYTES;
+          mbar_expect_tx(&full[s], a_from_tmem ? F_B_BYTES : F_STAGE_BYTES);
+          if (!a_from_tmem) tma_load_3d(st, &tm_oa, &full[s], kc * 64, row0, sample);
+          tma_load_2d(st + F_A_BYTES, &tm_wo, &full[s], kc * 64, g * F_NQ);
+          tma_load_2d(st + F_A_BYTES + F_NB * 128, &tm_wo, &full[s], kc * 64, g * F_NQ + F_NB);
+        }
       }
     }
   } else if (warp == 1) {
@@ -331,6 +393,7 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         auto issue_pv = [&](int j) {
           const int b = j & 1;
           const int ob = Cfg::NOBUF == 2 ? b : 0;
+          wd_wait(&v_full[j], 0, W_KV, abort_s);
           wd_wait(&p_full[b], (j >> 1) & 1, W_PFULL, abort_s);
           if (j >= Cfg::NOBUF) wd_wait(&o_free[ob], ((j / Cfg::NOBUF) - 1) & 1, W_OFREE, abort_s);
           tc_fence_after();
@@ -344,13 +407,13 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           }
           tc_commit(&o_full[b]);  // one barrier per warpgroup even when they share the accumulator
         };
-        wd_wait(kv_full, 0, W_KV, abort_s);
-        F_STAMP(4);
         wd_wait(qc_done, 0, W_QC, abort_s);
         tc_fence_after();
 #pragma unroll 1
         for (int j = 0; j < HG; ++j) {
           const int b = j & 1;
+          wd_wait(&k_full[j], 0, W_KV, abort_s);
+          if (j == 0) F_STAMP(4);
           const uint32_t sbuf = tmem_base + F_S_BASE + b * F_TKV;
           const uint32_t qb = tmem_base + j * Cfg::KQ2;
           const uint32_t sk = smem_u32(kv_s + j * Cfg::KV_HEAD_BYTES);
@@ -366,9 +429,36 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         issue_pv(HG - 1);
       }
       if (a.phases & 4) {
-        // ---- P5 (the producer only refills the ring after every O tile of the cluster is stored,
-        // which is after every S / P V of this CTA has been consumed: TMEM [0, 320) is free)
-        gemm_mmas(W_FULL5);
+        // ---- P5: out_g = O . Wo[g]^T into TMEM [192, 512) (S / O accumulators are dead by then; the
+        // bf16 attention output of this group occupies [0, 160) as the A operand of its own chunks)
+        const bool own_tmem = (a.phases & 2) != 0;
+        const uint32_t acc = tmem_base + F_ACC_BASE;
+        if (own_tmem) {
+          wd_wait(obf_done, 0, W_OBF, abort_s);
+          tc_fence_after();
+        }
+        for (int i = 0; i < KC; ++i, ++it) {
+          const bool a_from_tmem = own_tmem && i < 5;
+          const int s = it % F_STAGES;
+          wd_wait(&full[s], (it / F_STAGES) & 1, W_FULL5, abort_s);
+          tc_fence_after();
+          const uint32_t st = smem_u32(arena + s * F_STAGE_BYTES);
+          const uint64_t ad = umma_desc_sw128(st, 16, 1024);
+          const uint64_t b0 = umma_desc_sw128(st + F_A_BYTES, 16, 1024);
+          const uint64_t b1 = umma_desc_sw128(st + F_A_BYTES + F_NB * 128, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (a_from_tmem) {
+              const uint32_t at = tmem_base + 32 * i + 8 * k;  // 64 channels = 32 packed columns per chunk
+              mma_f16_ts(acc, at, b0 + 2 * k, idesc_g, (i | k) != 0);
+              mma_f16_ts(acc + F_NB, at, b1 + 2 * k, idesc_g, (i | k) != 0);
+            } else {
+              mma_f16_ss(acc, ad + 2 * k, b0 + 2 * k, idesc_g, (i | k) != 0);
+              mma_f16_ss(acc + F_NB, ad + 2 * k, b1 + 2 * k, idesc_g, (i | k) != 0);
+            }
+          }
+          tc_commit(&empty[s]);
+        }
         tc_commit(out_full);
       }
     }
@@ -493,8 +583,9 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         wd_wait(&o_full[wg], (j >> 1) & 1, W_OFULL, abort_s);
         tc_fence_after();
         if (stamp) F_STAMP(10 + 4 * j);
-        if (j >= 2) wd_wait(&ost_free[wg], ((j >> 1) - 1) & 1, W_OSTFREE, abort_s);
+        if (a.store_attn && j >= 2) wd_wait(&ost_free[wg], ((j >> 1) - 1) & 1, W_OSTFREE, abort_s);
         const uint64_t inv2 = f2_pack(inv, inv);
+        const uint32_t obf = tq + j * (DH / 2);  // this head's bf16 output: over its own (dead) bf16 Q
         constexpr int NCH = Cfg::NPV / 16;
         constexpr int EPI_CH = 4;
 #pragma unroll
@@ -521,19 +612,34 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
                           hi);
                 pk[k] = pack_bf16x2(lo, hi);
               }
-              uint8_t* chunk = stage + (c >> 2) * F_Q_CHUNK;
-              *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3))) =
-                  make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3) + 1)) =
-                  make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              // A operand of this group's own to_out chunks (16 c + 16 <= d, or the 8-column tail of d = 40)
+              if (16 * c + 16 <= DH) {
+                tmem_st_x8(obf + 8 * c, pk);
+              } else {
+                const uint32_t p4[4] = {pk[0], pk[1], pk[2], pk[3]};
+                tmem_st_x4(obf + 8 * c, p4);
+              }
+              if (a.store_attn) {
+                uint8_t* chunk = stage + (c >> 2) * F_Q_CHUNK;
+                *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3))) =
+                    make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3) + 1)) =
+                    make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              }
             }
           }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ost_full[wg]);
+        if (a.store_attn) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ost_full[wg]);
+        }
         if (stamp) F_STAMP(11 + 4 * j);
       }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(obf_done);
     }
 
     if (a.phases & 4) {
@@ -542,33 +648,52 @@ k3f_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       wd_wait(out_full, 0, W_OUTFULL, abort_s);
       tc_fence_after();
       if (threadIdx.x == 64) F_STAMP(50);
-#pragma unroll
-      for (int b5 = 0; b5 < 2; ++b5) {
-        uint32_t v[5][16];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) tmem_ld_x16(tq + 16 * (10 * wg + 5 * b5 + q), v[q]);
-        tmem_ld_wait();
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const int c = 10 * wg + 5 * b5 + q;  // 16-column group of the 320
-          uint32_t pk[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            pk[k] = pack_bf16x2(__uint_as_float(v[q][2 * k]) + bias_s[16 * c + 2 * k],
-                                __uint_as_float(v[q][2 * k + 1]) + bias_s[16 * c + 2 * k + 1]);
-          uint8_t* chunk = arena + (c >> 2) * F_Q_CHUNK;
-          *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(chunk + sw128_offset(row, 2 * (c & 3) + 1)) =
-              make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      // 20 column groups of 16 = 5 staging chunks of 64 columns.  Warpgroup 0 takes groups 0-9, warpgroup 1
+      // groups 10-19; every chunk leaves through its own TMA store as soon as its four groups are staged,
+      // so the stores read shared memory while the later chunks are still being converted.
+      const uint32_t tacc = tq + F_ACC_BASE;
+      if (wg == 0) {
+        p6_groups<4>(tacc, 0, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(4, 128);
+        if (threadIdx.x == 64) {
+          tma_store_4d(&tm_out, arena, 0, g, row0, sample);
+          tma_store_commit();
         }
-      }
-      fence_proxy_async_smem();
-      named_bar_sync(2, 256);
-      if (threadIdx.x == 64) {
-#pragma unroll
-        for (int c = 0; c < F_NQ / 64; ++c) tma_store_4d(&tm_out, arena + c * F_Q_CHUNK, c * 64, g, row0, sample);
-        tma_store_commit();
-        tma_store_wait_all();
+        p6_groups<4>(tacc, 4, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(4, 128);
+        if (threadIdx.x == 64) {
+          tma_store_4d(&tm_out, arena + F_Q_CHUNK, 64, g, row0, sample);
+          tma_store_commit();
+        }
+        p6_groups<2>(tacc, 8, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 256);  // chunk 2 is shared with warpgroup 1
+        if (threadIdx.x == 64) {
+          tma_store_4d(&tm_out, arena + 2 * F_Q_CHUNK, 128, g, row0, sample);
+          tma_store_commit();
+          tma_store_wait_read<0>();  // shared memory may go away; the writes complete with the grid
+        }
+      } else {
+        p6_groups<2>(tacc, 10, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 256);
+        p6_groups<4>(tacc, 12, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(5, 128);
+        if (threadIdx.x == 192) {
+          tma_store_4d(&tm_out, arena + 3 * F_Q_CHUNK, 192, g, row0, sample);
+          tma_store_commit();
+        }
+        p6_groups<4>(tacc, 16, bias_s, arena, row);
+        fence_proxy_async_smem();
+        named_bar_sync(5, 128);
+        if (threadIdx.x == 192) {
+          tma_store_4d(&tm_out, arena + 4 * F_Q_CHUNK, 256, g, row0, sample);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
       }
     }
   }
@@ -609,6 +734,7 @@ int launch_k3f(const CUtensorMap* tm, const FArgs& a, int n_tiles, int n_samples
 
 int g_k3f_phases = 7;
 int g_k3f_trace_on = 0;
+int g_k3f_keep_attn = 1;   // G == 1: also write the attention output when the caller passes a buffer
 
 }  // namespace
 }  // namespace fd
@@ -636,8 +762,7 @@ extern "C" int fd_cross_attn_fused(const void* x_bf16_dev, const void* wq_bf16_d
                                    int n_samples, int n_q, int heads, int d_head, int t_valid, int t_pad,
                                    float scale, void* attn_bf16_dev, void* out_bf16_dev, void* stream) {
   using namespace fd;
-  FD_REQUIRE(x_bf16_dev && wq_bf16_dev && kv_bf16_dev && ctx_index_dev && wo_bf16_dev && bo_bf16_dev &&
-                 attn_bf16_dev && out_bf16_dev,
+  FD_REQUIRE(x_bf16_dev && wq_bf16_dev && kv_bf16_dev && ctx_index_dev && wo_bf16_dev && bo_bf16_dev && out_bf16_dev,
              "fd_cross_attn_fused: NULL pointer");
   FD_REQUIRE(n_samples > 0 && n_q > 0 && heads > 0, "fd_cross_attn_fused: non-positive shape");
   FD_REQUIRE(d_head == 40 || d_head == 80 || d_head == 160,
@@ -653,7 +778,11 @@ extern "C" int fd_cross_attn_fused(const void* x_bf16_dev, const void* wq_bf16_d
   FD_REQUIRE(k_col_off + C <= kv_row_stride && v_col_off + C <= kv_row_stride,
              "fd_cross_attn_fused: K/V slice exceeds the cache row");
   FD_REQUIRE(kv_rows % t_pad == 0, "fd_cross_attn_fused: kv_rows=%lld not a multiple of t_pad", (long long)kv_rows);
-  const void* ptrs[7] = {x_bf16_dev, wq_bf16_dev, kv_bf16_dev, wo_bf16_dev, bo_bf16_dev, attn_bf16_dev, out_bf16_dev};
+  FD_REQUIRE(attn_bf16_dev || C == F_NQ,
+             "fd_cross_attn_fused: attn_bf16_dev may only be NULL when heads*d_head == %d (the head groups of wider "
+             "layers exchange their attention output through it)", F_NQ);
+  const void* ptrs[7] = {x_bf16_dev, wq_bf16_dev, kv_bf16_dev, wo_bf16_dev, bo_bf16_dev,
+                         attn_bf16_dev ? attn_bf16_dev : out_bf16_dev, out_bf16_dev};
   for (int i = 0; i < 7; ++i)
     FD_REQUIRE(reinterpret_cast<uintptr_t>(ptrs[i]) % 16 == 0, "fd_cross_attn_fused: pointers must be 16-byte aligned");
   FD_REQUIRE(n_samples <= 65535 && (n_q + F_TQ - 1) / F_TQ <= 65535, "fd_cross_attn_fused: grid limits");
@@ -669,7 +798,7 @@ extern "C" int fd_cross_attn_fused(const void* x_bf16_dev, const void* wq_bf16_d
     uint64_t strides[2] = {uC * 2, uN * uC * 2};
     uint32_t box[3] = {64, F_TQ, 1};
     rc = encode_tmap(&tm[which == 0 ? 0 : 5], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
-                     which == 0 ? x_bf16_dev : static_cast<const void*>(attn_bf16_dev), dims, strides, box,
+                     which == 0 ? x_bf16_dev : (attn_bf16_dev ? attn_bf16_dev : out_bf16_dev), dims, strides, box,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
@@ -697,7 +826,8 @@ extern "C" int fd_cross_attn_fused(const void* x_bf16_dev, const void* wq_bf16_d
     uint64_t dims[4] = {static_cast<uint64_t>(d_head), static_cast<uint64_t>(heads), uN, uS};
     uint64_t strides[3] = {static_cast<uint64_t>(d_head) * 2, uC * 2, uN * uC * 2};
     uint32_t box[4] = {64, 1, F_TQ, 1};
-    rc = encode_tmap(&tm[4], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, attn_bf16_dev, dims, strides, box,
+    rc = encode_tmap(&tm[4], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, attn_bf16_dev ? attn_bf16_dev : out_bf16_dev, dims,
+                     strides, box,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
@@ -720,6 +850,7 @@ extern "C" int fd_cross_attn_fused(const void* x_bf16_dev, const void* wq_bf16_d
   a.G = G;
   a.phases = g_k3f_phases | 1;
   a.trace = g_k3f_trace_on;
+  a.store_attn = (attn_bf16_dev != nullptr && (G > 1 || g_k3f_keep_attn || (a.phases & 6) != 6)) ? 1 : 0;
   a.scale_log2e = scale * 1.4426950408889634f;
   const int n_tiles = (n_q + F_TQ - 1) / F_TQ;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -160,9 +160,18 @@ class SelfAttention(nn.Module):
         return self.to_out[0](o.transpose(1, 2).reshape(B, N, C))
 
 
-# attn2 runs as ONE launch of K3F (to_q + attention + to_out + bias).  False restores round 1's
-# cuBLAS to_q -> K3 -> cuBLAS to_out sequence (kept for A/B timing and as a second parity witness).
-FUSED_ATTN2 = True
+# attn2 as ONE launch of K3F (to_q + attention + to_out + bias) or as round 1's cuBLAS to_q -> K3 ->
+# cuBLAS to_out sequence.  'auto' picks per site from the same-box A/B in profiles/r02/SUMMARY.md:
+# K3F wins wherever its grid fills the GPU with work per CTA that its serial phases amortise -- all
+# C = 320 sites, C = 640 between 4 and 16 samples -- and loses on the deep sites (C = 1280: 2-16 CTAs
+# at B = 1, each walking 2 x 20 k-chunks alone).  True / False force one path (tests, A/B).
+FUSED_ATTN2 = 'auto'
+
+
+def _use_fused_attn2(dim: int, n_samples: int) -> bool:
+    if FUSED_ATTN2 is True or FUSED_ATTN2 is False:
+        return FUSED_ATTN2
+    return dim == 320 or (dim == 640 and 4 <= n_samples <= 16)
 
 
 class CrossAttention(nn.Module):
@@ -180,13 +189,15 @@ class CrossAttention(nn.Module):
         self.v_col_off = -1
 
     def forward(self, x, kv: KVCache, ctx_index: torch.Tensor):
-        if FUSED_ATTN2 and self.dim % 320 == 0 and self.dim // self.heads in (40, 80, 160):
+        if self.dim % 320 == 0 and self.dim // self.heads in (40, 80, 160) \
+                and _use_fused_attn2(self.dim, x.shape[0]):
             if not x.is_contiguous():
                 x = x.contiguous()
             lin = self.to_out[0]
             out, _ = _native.cross_attn_fused(x, self.to_q.weight, kv.kv, self.k_col_off,
                                               self.v_col_off, ctx_index, lin.weight, lin.bias,
-                                              self.heads, T_VALID, T_PAD, self.scale)
+                                              self.heads, T_VALID, T_PAD, self.scale,
+                                              want_attn=False)
             return out
         q = self.to_q(x)
         if not q.is_contiguous():
@@ -543,10 +554,14 @@ class UNetGraphRunner:
                          temb_sin=self.static_temb).sample
 
     def load(self, owner, kv: KVCache, ctx_index: torch.Tensor):
-        if self.owner is not owner:
+        # keyed on the guide AND on the cache tensor it hands over: a guide rebuilds its cache
+        # when its embeddings / CFG layout change
+        key = (kv.kv.data_ptr(), kv.kv._version, ctx_index.data_ptr())
+        if self.owner is not owner or self.__dict__.get('_loaded') != key:
             self.kv.kv.copy_(kv.kv)
             self.ctx_index.copy_(ctx_index)
             self.owner = owner
+            self._loaded = key
 
     @torch.no_grad()
     def run(self, temb: torch.Tensor) -> torch.Tensor:

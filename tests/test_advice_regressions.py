@@ -81,7 +81,7 @@ def test_ddim_eta_with_host_generator(native, cuda_dev):
     pipe = FlexPipeline(vae, None, None, unet, prod.DDIMScheduler())
     lats = []
     for _ in range(2):
-        guide = SimpleGuide(_Enc(uncond), unet, 7.5, 3, embeds)
+        guide = SimpleGuide(_Enc(uncond), unet, 7.5, 4, embeds)
         lats.append(pipe(guide, init_size=(128, 128), eta=0.7,
                          generator=torch.Generator().manual_seed(11), output_type='latent',
                          return_dict=False))
