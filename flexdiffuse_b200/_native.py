@@ -21,6 +21,7 @@ FD_DTYPE_F32 = 0
 FD_DTYPE_BF16 = 1
 FD_BLEND_OK = 0
 FD_BLEND_ZERO_DIVISION = 1
+FD_BLEND_RANGE = 2
 
 # every symbol include/flexdiffuse_b200.h declares (tests check they all export)
 ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
@@ -29,7 +30,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_kv_project', 'fd_cross_attn', 'fd_cross_attn_fused',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
-               'fd_composite_eps')
+               'fd_composite_eps', 'fd_image_tail_u8')
 
 
 class NativeError(RuntimeError):
@@ -132,6 +133,8 @@ def lib() -> C.CDLL:
     l.fd_composite_eps.argtypes = [vp, C.c_int, C.POINTER(EntityBox), C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp, vp, vp]
     l.fd_composite_eps.restype = C.c_int
+    l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
+    l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
     l.fd_geglu.restype = C.c_int
     if l.fd_version() != FD_ABI_VERSION:
@@ -472,3 +475,20 @@ def composite_eps(eps_all: torch.Tensor, boxes: Sequence[EntityBox]):
     check(rc, 'fd_composite_eps')
     count_launch()
     return u, c
+
+
+# --------------------------------------------------------------------------- K10
+def image_tail_u8(image: torch.Tensor) -> torch.Tensor:
+    '''fd_image_tail_u8: decoder output [B,3,H,W] (f32 / bf16) -> uint8 [B,H,W,3] =
+    round(clamp(x / 2 + 0.5, 0, 1) * 255), the bytes PIL gets in flex.py:119-124.'''
+    if not image.is_cuda:
+        raise NativeError('image_tail_u8 needs a CUDA tensor; no fallback')
+    if not image.is_contiguous(memory_format=torch.channels_last):
+        image = image.contiguous(memory_format=torch.channels_last)
+    B, Cc, H, W = image.shape
+    out = torch.empty((B, H, W, Cc), dtype=torch.uint8, device=image.device)
+    rc = lib().fd_image_tail_u8(ptr(image), dtype_code(image.dtype), image.numel(), ptr(out),
+                                stream_ptr(image.device))
+    check(rc, 'fd_image_tail_u8')
+    count_launch()
+    return out

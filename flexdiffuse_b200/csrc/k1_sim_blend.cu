@@ -475,7 +475,13 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     K1_STAMP(6);
     // 2b. softmax over the T text tokens of each guide token (one thread per column; lanes walk
     //     consecutive addresses => conflict free)
-    for (int i = tid; i < A; i += K1_THREADS) {
+    // Columns beyond the first K1_THREADS (A = 257: the one remainder token) would cost every other
+    // thread a whole idle second pass: when there are at most K1_WARPS of them, one warp takes each,
+    // its lanes striding over the text tokens (same operations per element, so the same bits).
+    const int n_extra = A > K1_THREADS ? A - K1_THREADS : 0;
+    const bool extra_by_warp = n_extra > 0 && n_extra <= K1_WARPS;
+    const int a_thread = extra_by_warp ? K1_THREADS : A;
+    for (int i = tid; i < a_thread; i += K1_THREADS) {
       float mx = -INFINITY;
       for (int j = 0; j < T; ++j) mx = fmaxf(mx, pt_full[j * PT_STRIDE + i]);
       float s0 = 0.f, s1 = 0.f;
@@ -496,6 +502,35 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
       const float inv = 1.0f / (s0 + s1);
       float* simrow = (a.sim && blockIdx.y == 0) ? a.sim + (static_cast<size_t>(b_idx) * A + i) * T : nullptr;
       for (j = 0; j < T; ++j) {
+        const float p = pt_full[j * PT_STRIDE + i] * inv;
+        pt_full[j * PT_STRIDE + i] = p;
+        if (simrow) simrow[j] = p;
+      }
+    }
+    if (extra_by_warp && warp < n_extra) {
+      const int i = K1_THREADS + warp;
+      float mx = -INFINITY;
+      for (int j = lane; j < T; j += 32) mx = fmaxf(mx, pt_full[j * PT_STRIDE + i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      // the per-thread path sums even tokens into s0 and odd tokens into s1, in token order: lane 0
+      // repeats exactly that order over the exponentials the warp has just stored
+      for (int j = lane; j < T; j += 32) pt_full[j * PT_STRIDE + i] = ex2_approx(pt_full[j * PT_STRIDE + i] - mx);
+      __syncwarp();
+      float inv = 0.f;
+      if (lane == 0) {
+        float s0 = 0.f, s1 = 0.f;
+        int j = 0;
+        for (; j + 1 < T; j += 2) {
+          s0 += pt_full[j * PT_STRIDE + i];
+          s1 += pt_full[(j + 1) * PT_STRIDE + i];
+        }
+        if (j < T) s0 += pt_full[j * PT_STRIDE + i];
+        inv = 1.0f / (s0 + s1);
+      }
+      inv = __shfl_sync(0xffffffffu, inv, 0);
+      float* simrow = (a.sim && blockIdx.y == 0) ? a.sim + (static_cast<size_t>(b_idx) * A + i) * T : nullptr;
+      for (int j = lane; j < T; j += 32) {
         const float p = pt_full[j * PT_STRIDE + i] * inv;
         pt_full[j * PT_STRIDE + i] = p;
         if (simrow) simrow[j] = p;
@@ -806,7 +841,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
           if (a.map_idx) a.map_idx[bp * T + r] = sm.map_idx[r];
         }
       }
-      if (lane == 0 && a.status) a.status[bp] = status;
+      if (lane == 0 && a.status) a.status[bp] = sm.range_flag ? FD_BLEND_RANGE : status;
     }
     __syncthreads();
 
@@ -938,9 +973,9 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   FD_REQUIRE(workspace_dev && workspace_bytes >= fd_sim_blend_workspace_bytes(guide_batch, A, D),
              "fd_sim_blend: workspace too small (need fd_sim_blend_workspace_bytes)");
   FD_REQUIRE(reinterpret_cast<uintptr_t>(workspace_dev) % 16 == 0, "fd_sim_blend: workspace must be 16-byte aligned");
-  float* g_hi = static_cast<float*>(workspace_dev);
-  float* g_lo = g_hi + plane;
-  float* g_inv = g_lo + plane;
+  __half* g_hi = static_cast<__half*>(workspace_dev);   // fp16 h1 plane, h2 plane, then the fp32 inverse norms
+  __half* g_lo = g_hi + plane;
+  float* g_inv = reinterpret_cast<float*>(g_lo + plane);
   cudaStream_t cst = static_cast<cudaStream_t>(stream);
   {
     const int rows = guide_batch * A;
@@ -956,10 +991,11 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   for (int which = 0; which < 4; ++which) {
     // rows >= a_mma of a box are never used: keep them out of the map so TMA zero-fills them
     uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), static_cast<uint64_t>(guide_batch)};
-    uint64_t strides[2] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(A) * D * 4};
+    uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(A) * D * 2};
     uint32_t box[3] = {KC, static_cast<uint32_t>(which < 2 ? n_blk0 : (n_blk1 > 0 ? n_blk1 : 16)), 1};
     CUtensorMap* dst = which == 0 ? &tm_hi : which == 1 ? &tm_lo : which == 2 ? &tm_hi2 : &tm_lo2;
-    rc = encode_tmap(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (which & 1) ? g_lo : g_hi, dims, strides, box,
+    rc = encode_tmap(dst, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (which & 1) ? static_cast<const void*>(g_lo) : g_hi, dims,
+                     strides, box,
                      CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }

@@ -3,7 +3,8 @@
 `preprocess` (clip.py:15-39) and `CLIPEncoder.prompt / .image` (clip.py:47-100) keep the
 reference's signatures and numerics.  The transformer towers stay in PyTorch
 (transformers' CLIPModel); BASELINE.json's north_star only moves the similarity /
-blend stage that consumes these embeddings onto hand-written kernels (K1).
+blend stage that consumes these embeddings onto hand-written kernels (K1).  On a CUDA
+device each tower forward is captured once per input shape and replayed as a CUDA graph.
 '''
 from __future__ import annotations
 
@@ -35,10 +36,55 @@ def preprocess(image: Any) -> torch.Tensor:
     return 2.0 * torch.from_numpy(arr[None].transpose(0, 3, 1, 2)) - 1.0
 
 
+class _TowerGraph:
+    '''One CUDA-graph capture of a tower forward for a fixed input shape: the towers are ~300 (text)
+    and ~600 (vision) small eager launches at batch 1, i.e. launch-bound; replaying them as a graph
+    is what `Guide.embeds` calls per second are bounded by.  Same kernels, same
+    order, same numerics as the eager call.'''
+    def __init__(self, fn, example: torch.Tensor):
+        self.static_in = example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):
+                fn(self.static_in)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = fn(self.static_in)
+
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        self.static_in.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.static_out.clone()  # callers keep / edit the result (guidance.py:449, 467-472)
+
+
 class CLIPEncoder():
-    def __init__(self, clip, token) -> None:
+    def __init__(self, clip, token, cuda_graph: bool = True) -> None:
+        '''`cuda_graph` (not a reference argument): on a CUDA device, replay each tower as a captured
+        graph per input shape.  Call `invalidate()` after changing the CLIP weights.'''
         self.clip = clip
         self.token = token
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
+
+    def invalidate(self) -> None:
+        self._graphs = {}
+
+    def _run(self, kind: str, fn, x: torch.Tensor) -> torch.Tensor:
+        if not (self.cuda_graph and x.is_cuda) or torch.is_grad_enabled() \
+                or torch.cuda.is_current_stream_capturing():
+            return fn(x)
+        key = (kind, tuple(x.shape), x.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            try:
+                g = _TowerGraph(fn, x)
+            except Exception:  # a tower that cannot be captured still runs, un-graphed
+                torch.cuda.synchronize()
+                g = False
+            self._graphs[key] = g
+        return g(x) if g else fn(x)
 
     def prompt(self, prompt: str | List[str]) -> torch.Tensor:
         '''Final-layer-norm hidden states of the text tower, NOT projected
@@ -46,7 +92,8 @@ class CLIPEncoder():
         ids = self.token(prompt, padding='max_length',
                          max_length=self.token.model_max_length,
                          truncation=True, return_tensors='pt').input_ids
-        return self.clip.text_model(ids.to(self.clip.device))[0]
+        return self._run('text', lambda i: self.clip.text_model(i)[0],
+                         ids.to(self.clip.device))
 
     def image(self, image) -> torch.Tensor:
         '''All 257 vision tokens through post_layernorm and visual_projection
@@ -61,6 +108,9 @@ class CLIPEncoder():
         x = resize(x, [CLIP_IMAGE_SIZE, CLIP_IMAGE_SIZE],
                    interpolation=InterpolationMode.BICUBIC, antialias=True)
         x = normalize(x, list(_CLIP_MEAN), list(_CLIP_STD)).to(self.clip.device)
+        return self._run('image', self._vision, x)
+
+    def _vision(self, x: torch.Tensor) -> torch.Tensor:
         vm = self.clip.vision_model
         hidden = vm.pre_layrnorm(vm.embeddings(x))
         hidden = vm.encoder(inputs_embeds=hidden, output_attentions=False,

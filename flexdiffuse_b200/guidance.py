@@ -3,7 +3,7 @@ arithmetic on the B200:
 
     _map_emb        (guidance.py:23-85)    \
     _clustered_...  (guidance.py:135-172)   >  one launch of K1 `fd_sim_blend`
-    _blend_weights  (guidance.py:175-193)  /   (tcgen05 3xTF32 similarity GEMM, per-lane
+    _blend_weights  (guidance.py:175-193)  /   (tcgen05 split-fp16 similarity GEMM, per-lane
     Tweener.tween   (guidance.py:215-272) /     softmax, warp-shuffle mapping + weights, lerp)
     ConceptMapper   (guidance.py:275-312)      two more K1 mappings + a row scatter
     Guide           (guidance.py:315-474)      host glue, same signature and defaults
@@ -138,6 +138,8 @@ class Tweener():
                           f'Guidance Max: {self.max_guidance:.2%}')
                     print('Alt Embed Blend Weights:', res['weights'][b, 0].shape,
                           ':', res['weights'][b, 0].cpu())
+            if check and bool((status == _native.FD_BLEND_RANGE).any()):
+                raise ValueError('text embeddings outside the supported range (|x| < 1023, finite)')
             if check and bool(
                 (status == _native.FD_BLEND_ZERO_DIVISION).any()):
                 # two adjacent similarity peaks: guidance.py:111-112 divides by zero

@@ -49,6 +49,9 @@ extern "C" {
 #define FD_BLEND_OK            0
 #define FD_BLEND_ZERO_DIVISION 1   /* two adjacent similarity peaks: the reference raises
                                       ZeroDivisionError in guidance.py:111-112 */
+#define FD_BLEND_RANGE         2   /* a text embedding element with |x| >= 1023 (or non-finite): outside the
+                                      range of the fp16 two-term split of the similarity GEMM; the row
+                                      is not blended (CLIP hidden states stay below ~50)             */
 
 /* ---- library ----------------------------------------------------------------------- */
 
@@ -134,8 +137,9 @@ int fd_composite_eps(const void* eps_dev,            /* [2 + n_entities, C, H, W
  *                                                     header cap, 3-way select / lerp)
  * for `n_text` prompts against one shared guide (guide_batch == 1) or one guide per
  * prompt (guide_batch == n_text), and `n_params` parameter sets per prompt.
- * The similarity GEMM runs on tcgen05 (kind::tf32, 3-pass hi/lo split => fp32-equivalent
- * logits) with the accumulator in TMEM; softmax is per TMEM lane, the
+ * The similarity GEMM runs on tcgen05 (kind::f16 on a two-term fp16 split of both operands,
+ * three exact products => fp32-equivalent logits) with the accumulator in TMEM;
+ * softmax is per guide token, the
  * column arg-max and the weight heuristics are warp-shuffle code in the same kernel.   */
 typedef struct fd_tween_params {
   double threshold_floor;   /* Tweener.threshold_floor   guidance.py:205 */
@@ -162,7 +166,7 @@ int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddi
                  int n_text, int guide_batch,
                  int T,                      /* text tokens  (77; 2 <= T <= 80)                  */
                  int A,                      /* guide tokens (257 image / 77 text; 1 <= A <= 384)*/
-                 int D,                      /* embedding width (768; multiple of 32)            */
+                 int D,                      /* embedding width (768; multiple of 64)            */
                  const fd_tween_params* params_dev, /* DEVICE [n_params] (8-byte aligned)           */
                  const float* linear_weights_dev,   /* [n_params, T] torch.linspace, gd.py:231   */
                  int n_params,
@@ -176,7 +180,7 @@ int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddi
                  int64_t  workspace_bytes,
                  void* stream);
 
-/* Scratch needed by fd_sim_blend for the tf32 hi / lo planes and norms of the guide. */
+/* Scratch needed by fd_sim_blend for the split planes and norms of the guide (an upper bound). */
 int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D);
 
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
@@ -275,6 +279,17 @@ int fd_geglu(const void* in_bf16_dev,            /* [M, 2F]                     
              void*       out_bf16_dev,           /* [M, F]                                  */
              int64_t M, int F,                   /* F % 8 == 0                              */
              void* stream);
+
+/* ---- K10: image post-processing tail of the VAE decode ---------------------------------- *
+ * Replaces pipeline/flex.py:119-124 `(image / 2 + 0.5).clamp(0, 1)` -> `.cpu().permute(0,2,3,1)`
+ * -> numpy_to_pil's `(images * 255).round().astype('uint8')`.  `x` is the decoder output in
+ * channels-last memory order ([B, H, W, 3] flat); out[i] = round(clamp(x[i]/2 + 0.5, 0, 1) * 255)
+ * with the reference's rounding (tensor-dtype ops, fp32 product, round-half-even).          */
+int fd_image_tail_u8(const void* x_dev,      /* [n_elem] f32 or bf16, NHWC order               */
+                     int dtype,              /* FD_DTYPE_F32 / FD_DTYPE_BF16                   */
+                     int64_t n_elem,
+                     void* out_u8_dev,       /* [n_elem] uint8                                 */
+                     void* stream);
 
 #ifdef __cplusplus
 }

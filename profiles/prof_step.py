@@ -3,7 +3,7 @@
   ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off \
       --csv --log-file gpurun_out/launches.csv python profiles/prof_step.py step
   ncu --set full --clock-control none --import-source on --profile-from-start off \
-      -k regex:'k[1-4]_' -o gpurun_out/kernels python profiles/prof_step.py kernels
+      -k regex:'k[0-9]+f?_' -o gpurun_out/kernels python profiles/prof_step.py kernels
 
 `step`    : ONE denoising step of bench.py's workload (SD v1.5 UNet 512^2, B=1, CFG -> 2
             sample-forwards, eager so every kernel is named) + the fused K4 DDIM update.
@@ -70,20 +70,37 @@ def main(mode: str):
     k = _native.SchedCoeffs()
     k.guidance, k.use_cfg, k.a, k.b = 7.5, 1, 1.01, -0.05
     k.w[0] = 1.0
-    txt = torch.randn(1024, 77, 768, device=dev, generator=g)
-    img = torch.randn(1, 257, 768, device=dev, generator=g)
+    sys.path.insert(0, ROOT)
+    import bench  # the same planted K1 inputs as bench.py's roofline section
+    txt_h, img_h = bench._planted_pair(1024)
+    txt, img = txt_h.to(dev), img_h.to(dev)
     prm = _native.TweenParams()
-    prm.threshold_floor = prm.threshold_mult = prm.max_guidance = 0.5
+    prm.threshold_floor = prm.threshold_mult = prm.max_guidance = prm.clustered = 0.5
     prm.header_max, prm.align_mode, prm.mapping_reuse = 0.15, 1, 1
     lin = torch.linspace(0.0, 0.5, 77)[None].to(dev)
+    # K3F at bench.py's sample count (32 = configs[3]'s batch 16 with CFG), one site per width
+    S3 = 32
+    idx3 = torch.tensor([0] * 16 + [1] * 16, dtype=torch.int32, device=dev)
+    xs = [torch.randn(S3, {320: 4096, 640: 1024, 1280: 256}[m.dim], m.dim, device=dev,
+                      generator=g).bfloat16() for m in picks]
+    outs = [torch.empty_like(t) for t in xs]
+    scr = [torch.empty_like(t) if m.dim != 320 else None for m, t in zip(picks, xs)]
+    dec = torch.randn(1, 3, 512, 512, device=dev, generator=g).bfloat16().contiguous(
+        memory_format=torch.channels_last)
 
     def run():
         for m, q in zip(picks, qs):
             _native.cross_attn(q, kv.kv, m.k_col_off, m.v_col_off, idx, m.heads, 77, 80,
                                m.scale)
+        for m, t, o, sc in zip(picks, xs, outs, scr):
+            lin_o = m.to_out[0]
+            _native.cross_attn_fused(t, m.to_q.weight, kv.kv, m.k_col_off, m.v_col_off, idx3,
+                                     lin_o.weight, lin_o.bias, m.heads, 77, 80, m.scale, attn=sc,
+                                     out=o, want_attn=False)
         _native.cfg_sched_step(u, c, x, k, xo)
         unet.build_kv_cache(ctx9)
         _native.sim_blend(txt, img, [prm], lin)
+        _native.image_tail_u8(dec)
 
     run()
     torch.cuda.synchronize()
