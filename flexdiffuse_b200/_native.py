@@ -101,7 +101,7 @@ def lib() -> C.CDLL:
     l.fd_cfg_sched_step.restype = C.c_int
     l.fd_sim_blend.argtypes = [
         vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int,
-        vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp
+        vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp, vp
     ]
     l.fd_sim_blend.restype = C.c_int
     l.fd_sim_blend_workspace_bytes.argtypes = [C.c_int] * 3
@@ -272,7 +272,7 @@ def sim_blend(text: torch.Tensor,
                             ptr(params_dev),
                             ptr(linear_weights), P, ptr(out), ptr(map_s),
                             ptr(map_idx), ptr(weights), ptr(status), ptr(sim),
-                            ptr(ws), ws_bytes, stream_ptr(dev))
+                            ptr(ws), ws_bytes, C.cast(arr, C.c_void_p), stream_ptr(dev))
     count_launch()  # guide prep kernel
     check(rc, 'fd_sim_blend')
     count_launch()

@@ -60,6 +60,8 @@ constexpr int B_ITEMS = (NPAD * 8 + TEXT_THREADS - 1) / TEXT_THREADS;        // 
 
 // development aid: CTA (0,0) records %globaltimer at its phase boundaries when set
 static long long* g_k1_timing = nullptr;
+static int g_k1_fast = 1;               // development aid: 0 forces the one-prompt-per-CTA kernel
+static int g_k1_fast_min_prompts = 64;  // below this the per-prompt kernel fills the GPU better
 __device__ __forceinline__ long long k1_gtime() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -162,6 +164,307 @@ __device__ __forceinline__ int warp_consume_all_unused(unsigned int* used, int A
   return hi;
 }
 
+// per-prompt mapping / weight state in shared memory, shared by both main kernels
+struct K1MapView {
+  float* map_s;
+  int* map_idx;
+  float* iw;
+  int* sel;
+  float* slerp_a;
+  float* slerp_b;
+};
+
+// 4. weights for T <= 96 tokens in ONE warp (token r = lane + 32 k): linspace, Clustered, Threshold,
+// header cap, max_guidance, 3-way select; writes iw / sel for the blend and the optional outputs.
+__device__ __forceinline__ void k1_weights_warp(const fd_tween_params& prm, const K1MapView& mv, const float* lin_w,
+                                                int T, int lane, size_t bp, const K1Args& a, int range_flag) {
+    constexpr int KR = 3;  // 96 >= MAXT tokens
+    double s_d[KR];
+    float w[KR];
+    for (int k = 0; k < KR; ++k) {
+      const int r = lane + 32 * k;
+      s_d[k] = (r < T) ? static_cast<double>(mv.map_s[r]) : 0.0;
+      w[k] = (r < T) ? lin_w[r] : 0.f;
+    }
+    // avg_similarity = mapped_tokens[:, 1].mean()  (guidance.py:219): numpy float64 pairwise sum
+    double avg;
+    {
+      double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      double res = 0.0;
+      if (lane == 0) {
+        if (T < 8) {
+          for (int r = 0; r < T; ++r) res += static_cast<double>(mv.map_s[r]);
+        } else {
+          for (int q = 0; q < 8; ++q) acc[q] = static_cast<double>(mv.map_s[q]);
+          int r = 8;
+          for (; r < T - (T % 8); r += 8)
+            for (int q = 0; q < 8; ++q) acc[q] += static_cast<double>(mv.map_s[r + q]);
+          res = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+          for (; r < T; ++r) res += static_cast<double>(mv.map_s[r]);
+        }
+        res = res / static_cast<double>(T);
+      }
+      avg = __shfl_sync(0xffffffffu, res, 0);
+    }
+    int status = FD_BLEND_OK;
+    auto blend = [&](float (&aw)[KR], const float (&bw)[KR]) {
+      // _blend_weights (guidance.py:175-193): global-sign switch
+      float amax = -INFINITY, bmax = -INFINITY;
+      for (int k = 0; k < KR; ++k)
+        if (lane + 32 * k < T) {
+          amax = fmaxf(amax, aw[k]);
+          bmax = fmaxf(bmax, bw[k]);
+        }
+  #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+      }
+      for (int k = 0; k < KR; ++k) {
+        if (amax >= 0.f) {
+          if (bmax >= 0.f) aw[k] = fmaxf(aw[k], bw[k]);
+          else aw[k] = __fadd_rn(aw[k], bw[k]);
+        } else {
+          aw[k] = fminf(aw[k], bw[k]);
+        }
+      }
+    };
+
+    if (prm.clustered != 0.0) {
+      // _clustered_guidance (guidance.py:135-172)
+      unsigned int peak_mask[KR];
+      for (int k = 0; k < KR; ++k) {
+        const int r = lane + 32 * k;
+        bool pk = false;
+        if (r >= 1 && r <= T - 2) {
+          const double s = s_d[k];
+          const double sl = static_cast<double>(mv.map_s[r - 1]);
+          const double sr = static_cast<double>(mv.map_s[r + 1]);
+          pk = !(s < avg) && (sl <= s) && (s >= sr);
+        }
+        peak_mask[k] = __ballot_sync(0xffffffffu, pk);
+      }
+      const bool any_peak = (peak_mask[0] | peak_mask[1] | peak_mask[2]) != 0u;
+      if (any_peak) {
+        // adjacent peaks => valley lands on the next peak => d = 0 => ZeroDivisionError (Q6)
+        bool adj = false;
+        for (int k = 0; k < KR; ++k) {
+          if (peak_mask[k] & (peak_mask[k] >> 1)) adj = true;
+          if (k + 1 < KR && (peak_mask[k] >> 31) && (peak_mask[k + 1] & 1u)) adj = true;
+        }
+        if (adj) status = FD_BLEND_ZERO_DIVISION;
+        auto prev_peak = [&](int r) {  // largest peak index <= r, -1 if none
+          for (int k = r >> 5; k >= 0; --k) {
+            unsigned int m = peak_mask[k];
+            if (k == (r >> 5)) m &= (r & 31) == 31 ? 0xffffffffu : ((1u << ((r & 31) + 1)) - 1u);
+            if (m) return k * 32 + 31 - __clz(m);
+          }
+          return -1;
+        };
+        auto next_peak = [&](int r) {  // smallest peak index >= r, -1 if none
+          for (int k = r >> 5; k < KR; ++k) {
+            unsigned int m = peak_mask[k];
+            if (k == (r >> 5)) m &= ~((1u << (r & 31)) - 1u);
+            if (m) return k * 32 + __ffs(m) - 1;
+          }
+          return -1;
+        };
+        float cw[KR];
+        for (int k = 0; k < KR; ++k) {
+          const int r = lane + 32 * k;
+          float c = 1.0f;
+          if (r < T && !adj) {
+            const int pl = prev_peak(r), pr = next_peak(r);
+            if (r == 0) {
+              c = 0.0f;  // weights[0] -= slope (guidance.py:116-118); bl[0] is always 0
+            } else if (pl == r) {
+              c = 1.0f;
+            } else if (pl >= 0) {
+              const int vr = (pr >= 0) ? pl + (pr - pl + 1) / 2 : T - 1;  // p1 + ceil(d / 2)
+              if (r <= vr) {
+                const double g = 1.0 / static_cast<double>(vr - pl);       // traverse_right
+                c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(r - pl)));
+              } else {
+                const double g = 1.0 / static_cast<double>(pr - vr);       // traverse_left
+                c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(pr - r)));
+              }
+            } else {
+              const double g = 1.0 / static_cast<double>(pr);              // left of first peak
+              c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(pr - r)));
+            }
+          }
+          cw[k] = __fmul_rn(c, static_cast<float>(prm.clustered));
+        }
+        blend(w, cw);
+      }
+    }
+    if (prm.threshold_mult != 0.0) {
+      // guidance.py:241-246
+      float th[KR];
+      for (int k = 0; k < KR; ++k) th[k] = (s_d[k] < prm.threshold_floor) ? 0.f : static_cast<float>(prm.threshold_mult);
+      blend(w, th);
+    }
+    if (prm.header_max < 1.0 && lane == 0) {
+      // guidance.py:249-254
+      const double hw = static_cast<double>(w[0]);
+      w[0] = (hw >= 0.0) ? static_cast<float>(fmin(hw, prm.header_max)) : static_cast<float>(fmax(hw, -prm.header_max));
+    }
+    for (int k = 0; k < KR; ++k) {
+      const int r = lane + 32 * k;
+      if (r < T) {
+        // guidance.py:259-271
+        const double iw = fmin(static_cast<double>(w[k]), prm.max_guidance);
+        const double sd = 1.0 - s_d[k];
+        int sel = 2;
+        if (iw == 0.0) sel = 0;
+        else if (fabs(iw) >= sd) sel = 1;
+        mv.iw[r] = static_cast<float>(iw);
+        mv.sel[r] = sel;
+        if (a.weights) a.weights[bp * T + r] = w[k];
+        if (a.map_s) a.map_s[bp * T + r] = mv.map_s[r];
+        if (a.map_idx) a.map_idx[bp * T + r] = mv.map_idx[r];
+      }
+    }
+    if (lane == 0 && a.status) a.status[bp] = range_flag ? FD_BLEND_RANGE : status;
+}
+
+// 4b. slerp coefficients of the rows the reference would lerp (FD_BLEND_MODE_SLERP): one warp per row
+__device__ __forceinline__ void k1_slerp_rows(const K1MapView& mv, const float* text, const float* guide, int T, int D,
+                                              int wid, int nwarps, int lane) {
+    // ---------------- 4b. slerp coefficients of the rows the reference would lerp: one warp per
+    // row reduces <base,alt>, |base|^2, |alt|^2 in a fixed order, lane 0 turns them into
+    // sin((1-w)O)/sin O and sin(wO)/sin O.  Nearly parallel rows keep the lerp expression.
+    for (int r = wid; r < T; r += nwarps) {
+      if (mv.sel[r] != 2) continue;
+      const float4* bp4 = reinterpret_cast<const float4*>(text + static_cast<size_t>(r) * D);
+      const float4* ap4 = reinterpret_cast<const float4*>(guide + static_cast<size_t>(mv.map_idx[r]) * D);
+      float dot = 0.f, nb = 0.f, na = 0.f;
+      for (int c = lane; c < D / 4; c += 32) {
+        const float4 bv = __ldg(bp4 + c), av = __ldg(ap4 + c);
+        dot = fmaf(bv.x, av.x, fmaf(bv.y, av.y, fmaf(bv.z, av.z, fmaf(bv.w, av.w, dot))));
+        nb = fmaf(bv.x, bv.x, fmaf(bv.y, bv.y, fmaf(bv.z, bv.z, fmaf(bv.w, bv.w, nb))));
+        na = fmaf(av.x, av.x, fmaf(av.y, av.y, fmaf(av.z, av.z, fmaf(av.w, av.w, na))));
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        dot += __shfl_xor_sync(0xffffffffu, dot, o);
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        na += __shfl_xor_sync(0xffffffffu, na, o);
+      }
+      if (lane == 0) {
+        const float den = sqrtf(nb) * sqrtf(na);
+        const float cosv = den > 0.f ? dot / den : 1.0f;
+        if (fabsf(cosv) <= FD_SLERP_DOT_THRESHOLD) {
+          const float w = mv.iw[r];
+          const float theta = acosf(cosv), st = sinf(theta), tw = theta * w;
+          mv.slerp_a[r] = sinf(theta - tw) / st;
+          mv.slerp_b[r] = sinf(tw) / st;
+          mv.sel[r] = 3;
+        }
+      }
+    }
+}
+
+// 5. select / lerp of the [T, D] rows, 128-bit coalesced, `nthreads` threads (index `tid`), BU items
+// (= 2 BU 16-byte loads) in flight per thread
+template <int BU>
+__device__ __forceinline__ void k1_blend_rows(const K1MapView& mv, const float* text, const float* guide, float* outp,
+                                              int T, int D, int tid, int nthreads) {
+    const int d4 = D / 4;
+        for (int idx0 = tid; idx0 < T * d4; idx0 += BU * nthreads) {
+      float4 bv[BU], av[BU];
+      int sel[BU], rr[BU], cc[BU];
+  #pragma unroll
+      for (int u = 0; u < BU; ++u) {
+        const int idx = idx0 + u * nthreads;
+        sel[u] = -1;
+        if (idx < T * d4) {
+          rr[u] = idx / d4;
+          cc[u] = idx - rr[u] * d4;
+          sel[u] = mv.sel[rr[u]];
+          bv[u] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(rr[u]) * D) + cc[u]);
+          if (sel[u] != 0)
+            av[u] = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(mv.map_idx[rr[u]]) * D) + cc[u]);
+        }
+      }
+  #pragma unroll
+      for (int u = 0; u < BU; ++u) {
+        if (sel[u] < 0) continue;
+        const int r = rr[u];
+        float4 o = bv[u];
+        if (sel[u] == 1) {
+          o = av[u];
+        } else if (sel[u] == 3) {
+          const float ca = mv.slerp_a[r], cb = mv.slerp_b[r];
+          o.x = __fadd_rn(__fmul_rn(ca, bv[u].x), __fmul_rn(cb, av[u].x));
+          o.y = __fadd_rn(__fmul_rn(ca, bv[u].y), __fmul_rn(cb, av[u].y));
+          o.z = __fadd_rn(__fmul_rn(ca, bv[u].z), __fmul_rn(cb, av[u].z));
+          o.w = __fadd_rn(__fmul_rn(ca, bv[u].w), __fmul_rn(cb, av[u].w));
+        } else if (sel[u] == 2) {
+          const float w = mv.iw[r];
+          // base + (alt - base) * iw, every op rounded separately like the torch expression
+          o.x = __fadd_rn(bv[u].x, __fmul_rn(__fsub_rn(av[u].x, bv[u].x), w));
+          o.y = __fadd_rn(bv[u].y, __fmul_rn(__fsub_rn(av[u].y, bv[u].y), w));
+          o.z = __fadd_rn(bv[u].z, __fmul_rn(__fsub_rn(av[u].z, bv[u].z), w));
+          o.w = __fadd_rn(bv[u].w, __fmul_rn(__fsub_rn(av[u].w, bv[u].w), w));
+        }
+        __stcs(reinterpret_cast<float4*>(outp + static_cast<size_t>(r) * D) + cc[u], o);
+      }
+    }
+}
+
+// 5 (batched kernel). The same select / lerp, one WARP per row: the row's decision (sel, weight, guide index) is
+// warp-uniform, every lane owns the float4 columns lane, lane + 32, ... and keeps up to 6 text + 6 guide loads
+// in flight (a whole 3 KB row pair per warp at D = 768) with nothing but the data in registers.  The flat
+// item loop above needs per-item row / column / decision registers and spilled at 8 items per thread.
+__device__ __forceinline__ void k1_blend_rows_warp(const K1MapView& mv, const float* text, const float* guide,
+                                                   float* outp, int T, int D, int wid, int nwarps, int lane) {
+  const int d4 = D / 4;
+  constexpr int RU = 6;
+  for (int r = wid; r < T; r += nwarps) {
+    const int sel = mv.sel[r];
+    const float w = mv.iw[r];
+    const float4* bp4 = reinterpret_cast<const float4*>(text + static_cast<size_t>(r) * D);
+    const float4* ap4 = reinterpret_cast<const float4*>(guide + static_cast<size_t>(mv.map_idx[r]) * D);
+    float4* op4 = reinterpret_cast<float4*>(outp + static_cast<size_t>(r) * D);
+    const float ca = sel == 3 ? mv.slerp_a[r] : 0.f, cb = sel == 3 ? mv.slerp_b[r] : 0.f;
+    for (int c0 = lane; c0 < d4; c0 += 32 * RU) {
+      float4 bv[RU], av[RU];
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < d4) {
+          if (sel != 1) bv[u] = __ldg(bp4 + c);
+          if (sel != 0) av[u] = __ldg(ap4 + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RU; ++u) {
+        const int c = c0 + 32 * u;
+        if (c < d4) {
+          float4 o;
+          if (sel == 0) {
+            o = bv[u];
+          } else if (sel == 1) {
+            o = av[u];
+          } else if (sel == 3) {
+            o.x = __fadd_rn(__fmul_rn(ca, bv[u].x), __fmul_rn(cb, av[u].x));
+            o.y = __fadd_rn(__fmul_rn(ca, bv[u].y), __fmul_rn(cb, av[u].y));
+            o.z = __fadd_rn(__fmul_rn(ca, bv[u].z), __fmul_rn(cb, av[u].z));
+            o.w = __fadd_rn(__fmul_rn(ca, bv[u].w), __fmul_rn(cb, av[u].w));
+          } else {
+            // base + (alt - base) * iw, every op rounded separately like the torch expression
+            o.x = __fadd_rn(bv[u].x, __fmul_rn(__fsub_rn(av[u].x, bv[u].x), w));
+            o.y = __fadd_rn(bv[u].y, __fmul_rn(__fsub_rn(av[u].y, bv[u].y), w));
+            o.z = __fadd_rn(bv[u].z, __fmul_rn(__fsub_rn(av[u].z, bv[u].z), w));
+            o.w = __fadd_rn(bv[u].w, __fmul_rn(__fsub_rn(av[u].w, bv[u].w), w));
+          }
+          __stcs(op4 + c, o);
+        }
+      }
+    }
+  }
+}
+
 // guide fp32 -> 1 / |row|, and the two fp16 planes of (row / |row|) * 2^12 (normalise first, then
 // multiply, as the reference does: guidance.py:43-44).  One warp per row, the row stays in L1.
 __global__ void __launch_bounds__(256) k1_prep_guide_kernel(const float* __restrict__ g, __half* __restrict__ h1p,
@@ -214,6 +517,7 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   float* pt_full = reinterpret_cast<float*>(stage);  // [T][PT_STRIDE] logits, then probabilities
   float* pt = pt_full + PT_STRIDE;  // row r <-> text token r + 1 (header row dropped, guidance.py:55)
   K1Smem& sm = *reinterpret_cast<K1Smem*>(stage + a.stage_area);
+  const K1MapView mv = {sm.map_s, sm.map_idx, sm.iw, sm.sel, sm.slerp_a, sm.slerp_b};
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -694,239 +998,18 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
     if (p == p_begin) K1_STAMP(3);
     // ---------------- 4. weights: one warp, token r = lane + 32 k
     if (warp == 0) {
-      constexpr int KR = 3;  // 96 >= MAXT tokens
-      double s_d[KR];
-      float w[KR];
-      for (int k = 0; k < KR; ++k) {
-        const int r = lane + 32 * k;
-        s_d[k] = (r < T) ? static_cast<double>(sm.map_s[r]) : 0.0;
-        w[k] = (r < T) ? a.lin_w[static_cast<size_t>(p) * T + r] : 0.f;
-      }
-      // avg_similarity = mapped_tokens[:, 1].mean()  (guidance.py:219): numpy float64 pairwise sum
-      double avg;
-      {
-        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        double res = 0.0;
-        if (lane == 0) {
-          if (T < 8) {
-            for (int r = 0; r < T; ++r) res += static_cast<double>(sm.map_s[r]);
-          } else {
-            for (int q = 0; q < 8; ++q) acc[q] = static_cast<double>(sm.map_s[q]);
-            int r = 8;
-            for (; r < T - (T % 8); r += 8)
-              for (int q = 0; q < 8; ++q) acc[q] += static_cast<double>(sm.map_s[r + q]);
-            res = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-            for (; r < T; ++r) res += static_cast<double>(sm.map_s[r]);
-          }
-          res = res / static_cast<double>(T);
-        }
-        avg = __shfl_sync(0xffffffffu, res, 0);
-      }
-      int status = FD_BLEND_OK;
-      auto blend = [&](float (&aw)[KR], const float (&bw)[KR]) {
-        // _blend_weights (guidance.py:175-193): global-sign switch
-        float amax = -INFINITY, bmax = -INFINITY;
-        for (int k = 0; k < KR; ++k)
-          if (lane + 32 * k < T) {
-            amax = fmaxf(amax, aw[k]);
-            bmax = fmaxf(bmax, bw[k]);
-          }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-          bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
-        }
-        for (int k = 0; k < KR; ++k) {
-          if (amax >= 0.f) {
-            if (bmax >= 0.f) aw[k] = fmaxf(aw[k], bw[k]);
-            else aw[k] = __fadd_rn(aw[k], bw[k]);
-          } else {
-            aw[k] = fminf(aw[k], bw[k]);
-          }
-        }
-      };
-
-      if (prm.clustered != 0.0) {
-        // _clustered_guidance (guidance.py:135-172)
-        unsigned int peak_mask[KR];
-        for (int k = 0; k < KR; ++k) {
-          const int r = lane + 32 * k;
-          bool pk = false;
-          if (r >= 1 && r <= T - 2) {
-            const double s = s_d[k];
-            const double sl = static_cast<double>(sm.map_s[r - 1]);
-            const double sr = static_cast<double>(sm.map_s[r + 1]);
-            pk = !(s < avg) && (sl <= s) && (s >= sr);
-          }
-          peak_mask[k] = __ballot_sync(0xffffffffu, pk);
-        }
-        const bool any_peak = (peak_mask[0] | peak_mask[1] | peak_mask[2]) != 0u;
-        if (any_peak) {
-          // adjacent peaks => valley lands on the next peak => d = 0 => ZeroDivisionError (Q6)
-          bool adj = false;
-          for (int k = 0; k < KR; ++k) {
-            if (peak_mask[k] & (peak_mask[k] >> 1)) adj = true;
-            if (k + 1 < KR && (peak_mask[k] >> 31) && (peak_mask[k + 1] & 1u)) adj = true;
-          }
-          if (adj) status = FD_BLEND_ZERO_DIVISION;
-          auto prev_peak = [&](int r) {  // largest peak index <= r, -1 if none
-            for (int k = r >> 5; k >= 0; --k) {
-              unsigned int m = peak_mask[k];
-              if (k == (r >> 5)) m &= (r & 31) == 31 ? 0xffffffffu : ((1u << ((r & 31) + 1)) - 1u);
-              if (m) return k * 32 + 31 - __clz(m);
-            }
-            return -1;
-          };
-          auto next_peak = [&](int r) {  // smallest peak index >= r, -1 if none
-            for (int k = r >> 5; k < KR; ++k) {
-              unsigned int m = peak_mask[k];
-              if (k == (r >> 5)) m &= ~((1u << (r & 31)) - 1u);
-              if (m) return k * 32 + __ffs(m) - 1;
-            }
-            return -1;
-          };
-          float cw[KR];
-          for (int k = 0; k < KR; ++k) {
-            const int r = lane + 32 * k;
-            float c = 1.0f;
-            if (r < T && !adj) {
-              const int pl = prev_peak(r), pr = next_peak(r);
-              if (r == 0) {
-                c = 0.0f;  // weights[0] -= slope (guidance.py:116-118); bl[0] is always 0
-              } else if (pl == r) {
-                c = 1.0f;
-              } else if (pl >= 0) {
-                const int vr = (pr >= 0) ? pl + (pr - pl + 1) / 2 : T - 1;  // p1 + ceil(d / 2)
-                if (r <= vr) {
-                  const double g = 1.0 / static_cast<double>(vr - pl);       // traverse_right
-                  c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(r - pl)));
-                } else {
-                  const double g = 1.0 / static_cast<double>(pr - vr);       // traverse_left
-                  c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(pr - r)));
-                }
-              } else {
-                const double g = 1.0 / static_cast<double>(pr);              // left of first peak
-                c = __fsub_rn(1.0f, static_cast<float>(g * static_cast<double>(pr - r)));
-              }
-            }
-            cw[k] = __fmul_rn(c, static_cast<float>(prm.clustered));
-          }
-          blend(w, cw);
-        }
-      }
-      if (prm.threshold_mult != 0.0) {
-        // guidance.py:241-246
-        float th[KR];
-        for (int k = 0; k < KR; ++k) th[k] = (s_d[k] < prm.threshold_floor) ? 0.f : static_cast<float>(prm.threshold_mult);
-        blend(w, th);
-      }
-      if (prm.header_max < 1.0 && lane == 0) {
-        // guidance.py:249-254
-        const double hw = static_cast<double>(w[0]);
-        w[0] = (hw >= 0.0) ? static_cast<float>(fmin(hw, prm.header_max)) : static_cast<float>(fmax(hw, -prm.header_max));
-      }
-      for (int k = 0; k < KR; ++k) {
-        const int r = lane + 32 * k;
-        if (r < T) {
-          // guidance.py:259-271
-          const double iw = fmin(static_cast<double>(w[k]), prm.max_guidance);
-          const double sd = 1.0 - s_d[k];
-          int sel = 2;
-          if (iw == 0.0) sel = 0;
-          else if (fabs(iw) >= sd) sel = 1;
-          sm.iw[r] = static_cast<float>(iw);
-          sm.sel[r] = sel;
-          if (a.weights) a.weights[bp * T + r] = w[k];
-          if (a.map_s) a.map_s[bp * T + r] = sm.map_s[r];
-          if (a.map_idx) a.map_idx[bp * T + r] = sm.map_idx[r];
-        }
-      }
-      if (lane == 0 && a.status) a.status[bp] = sm.range_flag ? FD_BLEND_RANGE : status;
+      k1_weights_warp(prm, mv, a.lin_w + static_cast<size_t>(p) * T, T, lane, bp, a, sm.range_flag);
     }
     __syncthreads();
 
     if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
-      // ---------------- 4b. slerp coefficients of the rows the reference would lerp: one warp per
-      // row reduces <base,alt>, |base|^2, |alt|^2 in a fixed order, lane 0 turns them into
-      // sin((1-w)O)/sin O and sin(wO)/sin O.  Nearly parallel rows keep the lerp expression.
-      for (int r = warp; r < T; r += K1_THREADS / 32) {
-        if (sm.sel[r] != 2) continue;
-        const float4* bp4 = reinterpret_cast<const float4*>(text + static_cast<size_t>(r) * D);
-        const float4* ap4 = reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[r]) * D);
-        float dot = 0.f, nb = 0.f, na = 0.f;
-        for (int c = lane; c < D / 4; c += 32) {
-          const float4 bv = __ldg(bp4 + c), av = __ldg(ap4 + c);
-          dot = fmaf(bv.x, av.x, fmaf(bv.y, av.y, fmaf(bv.z, av.z, fmaf(bv.w, av.w, dot))));
-          nb = fmaf(bv.x, bv.x, fmaf(bv.y, bv.y, fmaf(bv.z, bv.z, fmaf(bv.w, bv.w, nb))));
-          na = fmaf(av.x, av.x, fmaf(av.y, av.y, fmaf(av.z, av.z, fmaf(av.w, av.w, na))));
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          dot += __shfl_xor_sync(0xffffffffu, dot, o);
-          nb += __shfl_xor_sync(0xffffffffu, nb, o);
-          na += __shfl_xor_sync(0xffffffffu, na, o);
-        }
-        if (lane == 0) {
-          const float den = sqrtf(nb) * sqrtf(na);
-          const float cosv = den > 0.f ? dot / den : 1.0f;
-          if (fabsf(cosv) <= FD_SLERP_DOT_THRESHOLD) {
-            const float w = sm.iw[r];
-            const float theta = acosf(cosv), st = sinf(theta), tw = theta * w;
-            sm.slerp_a[r] = sinf(theta - tw) / st;
-            sm.slerp_b[r] = sinf(tw) / st;
-            sm.sel[r] = 3;
-          }
-        }
-      }
+      k1_slerp_rows(mv, text, guide, T, D, warp, K1_WARPS, lane);
       __syncthreads();
     }
 
     if (p == p_begin) K1_STAMP(4);
     // ---------------- 5. select / lerp, 2 rows of 192 float4 per pass
-    {
-      const int d4 = D / 4;
-      float* outp = a.out + bp * T * D;
-      constexpr int BU = 4;  // items in flight per thread (one at a time left the phase latency-bound)
-      for (int idx0 = tid; idx0 < T * d4; idx0 += BU * K1_THREADS) {
-        float4 bv[BU], av[BU];
-        int sel[BU], rr[BU], cc[BU];
-#pragma unroll
-        for (int u = 0; u < BU; ++u) {
-          const int idx = idx0 + u * K1_THREADS;
-          sel[u] = -1;
-          if (idx < T * d4) {
-            rr[u] = idx / d4;
-            cc[u] = idx - rr[u] * d4;
-            sel[u] = sm.sel[rr[u]];
-            bv[u] = __ldg(reinterpret_cast<const float4*>(text + static_cast<size_t>(rr[u]) * D) + cc[u]);
-            if (sel[u] != 0)
-              av[u] = __ldg(reinterpret_cast<const float4*>(guide + static_cast<size_t>(sm.map_idx[rr[u]]) * D) + cc[u]);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < BU; ++u) {
-          if (sel[u] < 0) continue;
-          const int r = rr[u];
-          float4 o = bv[u];
-          if (sel[u] == 1) {
-            o = av[u];
-          } else if (sel[u] == 3) {
-            const float ca = sm.slerp_a[r], cb = sm.slerp_b[r];
-            o.x = __fadd_rn(__fmul_rn(ca, bv[u].x), __fmul_rn(cb, av[u].x));
-            o.y = __fadd_rn(__fmul_rn(ca, bv[u].y), __fmul_rn(cb, av[u].y));
-            o.z = __fadd_rn(__fmul_rn(ca, bv[u].z), __fmul_rn(cb, av[u].z));
-            o.w = __fadd_rn(__fmul_rn(ca, bv[u].w), __fmul_rn(cb, av[u].w));
-          } else if (sel[u] == 2) {
-            const float w = sm.iw[r];
-            // base + (alt - base) * iw, every op rounded separately like the torch expression
-            o.x = __fadd_rn(bv[u].x, __fmul_rn(__fsub_rn(av[u].x, bv[u].x), w));
-            o.y = __fadd_rn(bv[u].y, __fmul_rn(__fsub_rn(av[u].y, bv[u].y), w));
-            o.z = __fadd_rn(bv[u].z, __fmul_rn(__fsub_rn(av[u].z, bv[u].z), w));
-            o.w = __fadd_rn(bv[u].w, __fmul_rn(__fsub_rn(av[u].w, bv[u].w), w));
-          }
-          __stcs(reinterpret_cast<float4*>(outp + static_cast<size_t>(r) * D) + cc[u], o);
-        }
-      }
-    }
+    k1_blend_rows<4>(mv, text, guide, a.out + bp * T * D, T, D, tid, K1_THREADS);
     __syncthreads();
   }
 
@@ -939,6 +1022,528 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
   }
 }
 
+
+// =====================================================================================================
+// K1B -- the batched fast path (round 2): many prompts against ONE shared guide, mapping with reuse (or
+// DIRECT), which is what Guide.embeds / the sweep driver / bench.py run.  Same arithmetic contract as the
+// kernel above (its own similarity matrix within tolerance of the oracle's, every decision exact on
+// that matrix); what changes is where the work sits:
+//   * roles swapped: the GUIDE tokens are the M rows (two 128-row tiles = TMEM lanes), the text tokens
+//     of TWO prompts are the N = 160 columns.  One pass of the guide planes feeds two prompts (half the
+//     guide ingest per prompt), no padded lanes (77 of 80 columns, 256 of 256 rows are real), and the
+//     softmax over the text tokens becomes a per-lane row softmax in REGISTERS, straight out of TMEM:
+//     the [T][A] logits matrix, its transposition through shared memory and the four passes over it
+//     are gone.  Column arg-max over the guide tokens = one redux.sync.max.u32 on the float bits + one
+//     ballot per column per warp, then 8 partials per column.
+//   * persistent CTAs (one per SM, 512 threads) with dedicated roles, so the HBM-bound blend of batch b
+//     runs under the GEMM of batch b + 1:  warp 0 TMA (guide planes, 2-stage ring), warp 1 MMA issuer,
+//     warps 2-7 text feed (fp32 -> two fp16 planes, norms, the 257th guide token in exact fp32),
+//     warps 8-15 tail (TMEM drain + softmax + arg-max partials, weights, blend).
+// Everything the fast path cannot do (per-prompt guides, no-reuse greedy mappings, A <= 128 or > 264,
+// more than one remainder row, few prompts) stays on the kernel above.
+constexpr int KB_THREADS = 512;
+constexpr int KB_FEED_WARPS = 6;
+constexpr int KB_FEED_THREADS = KB_FEED_WARPS * 32;       // 192
+constexpr int KB_TAIL_WARPS = 8;
+constexpr int KB_TAIL_THREADS = KB_TAIL_WARPS * 32;       // 256
+constexpr int KB_NP = 2;                                  // prompts per batch
+constexpr int KB_NTXT = KB_NP * NPAD;                     // 160 = UMMA N
+constexpr int KB_G_PLANE = 256 * 128;                     // guide plane of a K chunk: 256 rows x 128 B
+constexpr int KB_T_PLANE = KB_NTXT * 128;                 // text plane: 160 rows x 128 B
+constexpr int KB_STAGE = 2 * KB_G_PLANE + 2 * KB_T_PLANE; // 106496
+constexpr int KB_STAGES = 2;
+constexpr int KB_ITEMS = (KB_NTXT * 8 + KB_FEED_THREADS - 1) / KB_FEED_THREADS;  // 7
+constexpr int KB_MT = MAXT + 16;
+constexpr int KB_PRM = 2;                                 // parameter sets cached in shared memory
+// development aid (fd_debug_set_k1_timing, buffer of >= 256 int64): CTA 0 stamps %globaltimer at
+// [64 + 16 b + e] for its first 8 batches: e = 0 tail sees norms, 1 accumulator complete, 2 TMEM drained,
+// 3 arg-max combined, 4 weights done, 5 blend done; 8 feed finished the batch; 9 MMA committed it
+#define KB_STAMP(bl, e)                                                                              \
+  do {                                                                                               \
+    if (a.timing && blockIdx.x == 0 && (bl) < 8) a.timing[64 + 16 * (bl) + (e)] = k1_gtime();        \
+  } while (0)
+
+struct KbPartials {
+  unsigned int v[KB_NP][KB_TAIL_WARPS][NPAD];  // per-warp column maxima (float bits)
+  int i[KB_NP][KB_TAIL_WARPS][NPAD];
+};
+struct KbMaps {
+  float map_s[KB_NP][KB_MT];
+  int map_idx[KB_NP][KB_MT];
+  float iw[KB_NP][KB_MT];
+  int sel[KB_NP][KB_MT];
+  float slerp_a[KB_NP][KB_MT], slerp_b[KB_NP][KB_MT];
+};
+struct KbSmem {
+  alignas(16) float sbn[2][KB_NP][NPAD];  // [slot] 100 log2e / (|text_j| 2^18): logits scale of column j
+  float rem[2][KB_NP][NPAD];          // [slot] <text_j / |text_j|, guide_rem>
+  float prem[KB_NP][NPAD];            // softmax row of the remainder guide token
+  float diag[KB_NP][NPAD];            // P[r, r + 1] (DIRECT order)
+  float amax_s[KB_NP][KB_MT];         // arg-max over the guide tokens per column
+  int amax_i[KB_NP][KB_MT];
+  // the arg-max partials die when amax_* is written; the mapping / weight state is born after that
+  union {
+    KbPartials part;
+    KbMaps m;
+  };
+  fd_tween_params prm[KB_PRM];        // the first parameter sets and their linspace rows, loaded once
+  float lin_w[KB_PRM][KB_MT];
+  int range_flag[2][KB_NP];
+  uint64_t full_bar[KB_STAGES], empty_bar[KB_STAGES], acc_full, acc_free, norm_full[2];
+  uint32_t tmem_slot;
+};
+constexpr int KB_SMEM_BYTES = 1024 + KB_STAGES * KB_STAGE + sizeof(KbSmem);
+static_assert(KB_SMEM_BYTES <= 227 * 1024, "K1B shared memory");
+
+__global__ void __launch_bounds__(KB_THREADS, 1)
+k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_h2,
+                     const K1Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                              ~static_cast<uintptr_t>(1023));
+  KbSmem& sm = *reinterpret_cast<KbSmem*>(stage + KB_STAGES * KB_STAGE);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int T = a.T, A = a.A, D = a.D;
+  const int num_kc = D / KC;
+  const int n_batches = (a.n_text + KB_NP - 1) / KB_NP;
+  const int my_batches = (n_batches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                         static_cast<int>(gridDim.x);
+  const int n_rem = A - a.a_mma;  // 0 or 1 on this path
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_h1);
+    tma_prefetch_desc(&tm_h2);
+    for (int st = 0; st < KB_STAGES; ++st) {
+      mbar_init(&sm.full_bar[st], 1 + KB_FEED_WARPS);
+      mbar_init(&sm.empty_bar[st], 1);
+    }
+    mbar_init(&sm.acc_full, 1);
+    mbar_init(&sm.acc_free, KB_TAIL_WARPS);
+    mbar_init(&sm.norm_full[0], KB_FEED_WARPS);
+    mbar_init(&sm.norm_full[1], KB_FEED_WARPS);
+    for (int q = 0; q < 2 * KB_NP; ++q) (&sm.range_flag[0][0])[q] = 0;
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&sm.tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm.tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================ TMA producer: guide planes
+    if (elect_one()) {
+      const int total = my_batches * num_kc;
+      for (int g = 0; g < total; ++g) {
+        const int st = g % KB_STAGES, kc = g % num_kc;
+        mbar_wait_backoff(&sm.empty_bar[st], ((g / KB_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&sm.full_bar[st], 2u * KB_G_PLANE);
+        uint8_t* base = stage + st * KB_STAGE;
+        tma_load_3d(base, &tm_h1, &sm.full_bar[st], kc * KC, 0, 0);
+        tma_load_3d(base + KB_G_PLANE, &tm_h2, &sm.full_bar[st], kc * KC, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_F16, 128, KB_NTXT, 0, 0);
+      int g = 0;
+      for (int b = 0; b < my_batches; ++b) {
+        if (b > 0) mbar_wait_backoff(&sm.acc_free, (b - 1) & 1);  // the tail has drained batch b - 1
+        tc_fence_after();
+        for (int kc = 0; kc < num_kc; ++kc, ++g) {
+          const int st = g % KB_STAGES;
+          mbar_wait_backoff(&sm.full_bar[st], (g / KB_STAGES) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(stage + st * KB_STAGE);
+          const uint64_t th1 = umma_desc_sw128(base + 2 * KB_G_PLANE, 16, 1024);
+          const uint64_t th2 = umma_desc_sw128(base + 2 * KB_G_PLANE + KB_T_PLANE, 16, 1024);
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            const uint64_t gh1 = umma_desc_sw128(base + t * 128 * 128, 16, 1024);
+            const uint64_t gh2 = umma_desc_sw128(base + KB_G_PLANE + t * 128 * 128, 16, 1024);
+            const uint32_t d = tmem_base + t * KB_NTXT;
+#pragma unroll
+            for (int ks = 0; ks < KC / 16; ++ks) {  // small terms first
+              mma_f16_ss(d, gh2 + 2 * ks, th1 + 2 * ks, idesc, (kc | ks) != 0);
+              mma_f16_ss(d, gh1 + 2 * ks, th2 + 2 * ks, idesc, 1);
+              mma_f16_ss(d, gh1 + 2 * ks, th1 + 2 * ks, idesc, 1);
+            }
+          }
+          tc_commit(&sm.empty_bar[st]);
+        }
+        tc_commit(&sm.acc_full);
+        KB_STAMP(b, 9);
+      }
+    }
+  } else if (warp < 2 + KB_FEED_WARPS) {
+    // ================================================================ text feed
+    const int tt = tid - 64;
+    float4 rb[KB_ITEMS][2];
+    float ssb[KB_ITEMS], racc[KB_ITEMS];
+    const float* grem = a.guide + static_cast<size_t>(a.a_mma) * D + (tt & 7) * 8;
+    float4 gq0 = make_float4(0.f, 0.f, 0.f, 0.f), gq1 = gq0;
+    const int total = my_batches * num_kc;
+    auto load_chunk = [&](int g) {
+      const int b = static_cast<int>(blockIdx.x) + (g / num_kc) * static_cast<int>(gridDim.x), kc = g % num_kc;
+      if (n_rem == 1) {
+        gq0 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
+        gq1 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC) + 1);
+      }
+#pragma unroll
+      for (int j = 0; j < KB_ITEMS; ++j) {
+        const int f = tt + j * KB_FEED_THREADS;
+        const int row = f >> 3, pp = row / NPAD, rr = row - pp * NPAD;
+        const int prompt = b * KB_NP + pp;
+        if (f < KB_NTXT * 8 && rr < T && prompt < a.n_text) {
+          const float4* src = reinterpret_cast<const float4*>(a.text + (static_cast<size_t>(prompt) * T + rr) * D + kc * KC) +
+                              2 * (f & 7);
+          rb[j][0] = __ldg(src);
+          rb[j][1] = __ldg(src + 1);
+        } else {
+          rb[j][0] = rb[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    if (total > 0) load_chunk(0);
+    bool oor0 = false, oor1 = false;
+    for (int g = 0; g < total; ++g) {
+      const int st = g % KB_STAGES, kc = g % num_kc, bl = g / num_kc;
+      if (kc == 0) {
+#pragma unroll
+        for (int j = 0; j < KB_ITEMS; ++j) ssb[j] = racc[j] = 0.f;
+        oor0 = oor1 = false;
+      }
+      mbar_wait_backoff(&sm.empty_bar[st], ((g / KB_STAGES) & 1) ^ 1);  // 192 spinning threads would starve the tail
+      uint8_t* t_h1 = stage + st * KB_STAGE + 2 * KB_G_PLANE;
+      uint8_t* t_h2 = t_h1 + KB_T_PLANE;
+#pragma unroll
+      for (int j = 0; j < KB_ITEMS; ++j) {
+        const int f = tt + j * KB_FEED_THREADS;
+        if (f < KB_NTXT * 8) {
+          const float x[8] = {rb[j][0].x, rb[j][0].y, rb[j][0].z, rb[j][0].w,
+                              rb[j][1].x, rb[j][1].y, rb[j][1].z, rb[j][1].w};
+          uint32_t ph[4], pl[4];
+          bool bad = false;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float x0 = x[2 * q] * TEXT_SCALE, x1 = x[2 * q + 1] * TEXT_SCALE;
+            bad |= !(fabsf(x0) < 65504.f) | !(fabsf(x1) < 65504.f);
+            const __half a0 = __float2half_rn(x0), a1 = __float2half_rn(x1);
+            const __half b0 = __float2half_rn(x0 - __half2float(a0)), b1 = __float2half_rn(x1 - __half2float(a1));
+            ph[q] = static_cast<uint32_t>(__half_as_ushort(a0)) | (static_cast<uint32_t>(__half_as_ushort(a1)) << 16);
+            pl[q] = static_cast<uint32_t>(__half_as_ushort(b0)) | (static_cast<uint32_t>(__half_as_ushort(b1)) << 16);
+          }
+          oor0 |= bad && (f >> 3) < NPAD;
+          oor1 |= bad && (f >> 3) >= NPAD;
+          const uint32_t off = sw128_offset(f >> 3, f & 7);
+          *reinterpret_cast<uint4*>(t_h1 + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+          *reinterpret_cast<uint4*>(t_h2 + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+          float ss = ssb[j], ra = racc[j];
+          const float gq[8] = {gq0.x, gq0.y, gq0.z, gq0.w, gq1.x, gq1.y, gq1.z, gq1.w};
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            ss += x[q] * x[q];
+            ra = fmaf(x[q], gq[q], ra);
+          }
+          ssb[j] = ss;
+          racc[j] = ra;
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.full_bar[st]);
+      if (g + 1 < total) load_chunk(g + 1);  // in flight while the MMAs of this chunk run
+      if (kc == num_kc - 1) {
+        // end of a batch: column scales, remainder dot products, range flags -> the tail warps
+        const int slot = bl & 1;
+#pragma unroll
+        for (int j = 0; j < KB_ITEMS; ++j) {
+          float ss = ssb[j], rs = racc[j];
+          ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+          ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+          rs += __shfl_xor_sync(0xffffffffu, rs, 1);
+          rs += __shfl_xor_sync(0xffffffffu, rs, 2);
+          rs += __shfl_xor_sync(0xffffffffu, rs, 4);
+          const int f = tt + j * KB_FEED_THREADS;
+          if ((f & 7) == 0 && f < KB_NTXT * 8) {
+            const int row = f >> 3, pp = row / NPAD, rr = row - pp * NPAD;
+            sm.sbn[slot][pp][rr] = (1.0f / sqrtf(ss)) * (100.0f * 1.4426950408889634f / (TEXT_SCALE * GUIDE_SCALE));
+            sm.rem[slot][pp][rr] = rs * (1.0f / sqrtf(ss));
+          }
+        }
+        if (oor0) sm.range_flag[slot][0] = 1;
+        if (oor1) sm.range_flag[slot][1] = 1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.norm_full[slot]);
+        if (tt == 0) KB_STAMP(bl, 8);
+      }
+    }
+  } else {
+    // ================================================================ tail: softmax, mapping, weights, blend
+    const int tw = warp - (2 + KB_FEED_WARPS);          // 0..7
+    const int ttid = tid - (2 + KB_FEED_WARPS) * 32;    // 0..255
+    const int tile = tw >> 2, quarter = tw & 3;
+    const int gi = tile * 128 + quarter * 32 + lane;    // guide token of this thread's TMEM lane
+    const bool gi_valid = gi < a.a_mma;
+    const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + tile * KB_NTXT;
+    const int ncol = T - 1;
+    const float inv_na_rem = n_rem == 1 ? a.inv_norm_a[a.a_mma] : 0.f;
+    for (int idx = ttid; idx < KB_PRM * KB_MT; idx += KB_TAIL_THREADS) {
+      const int q = idx / KB_MT, r = idx - q * KB_MT;
+      if (q < a.n_params) {
+        if (r == 0) sm.prm[q] = a.params[q];
+        sm.lin_w[q][r] = r < T ? a.lin_w[static_cast<size_t>(q) * T + r] : 0.f;
+      }
+    }
+    named_bar_sync(1, KB_TAIL_THREADS);
+    for (int bl = 0; bl < my_batches; ++bl) {
+      const int b = static_cast<int>(blockIdx.x) + bl * static_cast<int>(gridDim.x);
+      const int slot = bl & 1;
+      const int n_here = min(KB_NP, a.n_text - b * KB_NP);
+      if (ttid < KB_NP) sm.range_flag[slot ^ 1][ttid] = 0;  // the feed of batch bl + 1 starts from a clean flag
+      mbar_wait(&sm.norm_full[slot], (bl >> 1) & 1);
+      if (ttid == 0) KB_STAMP(bl, 0);
+      mbar_wait(&sm.acc_full, bl & 1);
+      tc_fence_after();
+      if (ttid == 0) KB_STAMP(bl, 1);
+      // ---- 2. drain TMEM: per guide token (lane) the 80 logits of each prompt, softmax in registers
+      // Three passes over the prompt's 80 TMEM columns, 16 at a time (row max; 2^(l - max) written back
+      // over the logits + row sum; normalise + arg-max), so only 16 values are live in registers: holding
+      // all 80 made the compiler spill and rematerialise its way through the arg-max loop (12 us / prompt).
+      const int gi_base = gi - lane;
+#ifdef KB_X_SKIP_DRAIN
+      if (false)
+#endif
+      for (int pp = 0; pp < n_here; ++pp) {
+        const uint32_t tp = tlane + NPAD * pp;
+        const float* sbn = sm.sbn[slot][pp];
+        // (next chunk's TMEM load is issued before the current one is processed; the 80 column scales
+        // come in as 20 float4: rows of sbn are 16-byte aligned)
+        float mx = -INFINITY;
+        {
+          uint32_t v[2][16];
+          tmem_ld_x16(tp, v[0]);
+#pragma unroll
+          for (int c = 0; c < NPAD / 16; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NPAD / 16) tmem_ld_x16(tp + 16 * (c + 1), v[(c + 1) & 1]);
+            const float4 q0 = *reinterpret_cast<const float4*>(&sbn[16 * c]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sbn[16 * c + 4]);
+            const float4 q2 = *reinterpret_cast<const float4*>(&sbn[16 * c + 8]);
+            const float4 q3 = *reinterpret_cast<const float4*>(&sbn[16 * c + 12]);
+            const float sc[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                                  q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+              if (16 * c + k < T) mx = fmaxf(mx, __fmul_rn(__uint_as_float(v[c & 1][k]), sc[k]));
+          }
+        }
+        float s0 = 0.f, s1 = 0.f;
+        {
+          uint32_t v[2][16];
+          tmem_ld_x16(tp, v[0]);
+#pragma unroll
+          for (int c = 0; c < NPAD / 16; ++c) {
+            tmem_ld_wait();
+            if (c + 1 < NPAD / 16) tmem_ld_x16(tp + 16 * (c + 1), v[(c + 1) & 1]);
+            const float4 q0 = *reinterpret_cast<const float4*>(&sbn[16 * c]);
+            const float4 q1 = *reinterpret_cast<const float4*>(&sbn[16 * c + 4]);
+            const float4 q2 = *reinterpret_cast<const float4*>(&sbn[16 * c + 8]);
+            const float4 q3 = *reinterpret_cast<const float4*>(&sbn[16 * c + 12]);
+            const float sc[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                                  q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+            uint32_t e8[2][8];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int j = 16 * c + k;
+              const float e = j < T ? ex2_approx(__fmul_rn(__uint_as_float(v[c & 1][k]), sc[k]) - mx) : 0.f;
+              if (k & 1) s1 += e;
+              else s0 += e;
+              e8[k >> 3][k & 7] = __float_as_uint(e);
+            }
+            tmem_st_x8(tp + 16 * c, e8[0]);
+            tmem_st_x8(tp + 16 * c + 8, e8[1]);
+          }
+        }
+        tmem_st_wait();
+        const float inv = 1.0f / (s0 + s1);
+        float dg = 0.f;
+        unsigned int keep_v[3] = {0u, 0u, 0u};
+        int keep_i[3] = {-1, -1, -1};
+        float* simrow = (a.sim && gi_valid) ? a.sim + (static_cast<size_t>(b * KB_NP + pp) * A + gi) * T : nullptr;
+        // opaque copies: without them the compiler re-derives lane / guide index from %tid.x for every column
+        int lane_k = lane, gi_k = gi, gb_k = gi_base;
+        asm volatile("" : "+r"(lane_k), "+r"(gi_k), "+r"(gb_k));
+        const unsigned int vmask = gi_valid ? 0xffffffffu : 0u;
+        uint32_t v3[2][16];
+        tmem_ld_x16(tp, v3[0]);
+#pragma unroll
+        for (int c = 0; c < NPAD / 16; ++c) {
+          tmem_ld_wait();
+          if (c + 1 < NPAD / 16) tmem_ld_x16(tp + 16 * (c + 1), v3[(c + 1) & 1]);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int j = 16 * c + k;
+            const float pv = __uint_as_float(v3[c & 1][k]) * inv;  // columns j >= T hold e = 0: harmless, never stored
+            if (simrow && j < T) simrow[j] = pv;
+            if (j >= 1) {
+              const int r = j - 1;  // column r <-> text token r + 1
+              dg = (gi_k == r) ? pv : dg;
+#ifndef KB_X_SKIP_ARGMAX
+              // arg-max over this warp's 32 guide tokens: positive floats order like their bits
+              const unsigned int bits = __float_as_uint(pv) & vmask;
+              const unsigned int m = __reduce_max_sync(0xffffffffu, bits);
+              const unsigned int eq = __ballot_sync(0xffffffffu, bits == m) & __ballot_sync(0xffffffffu, vmask != 0u);
+              const bool mine = lane_k == (r & 31);
+              keep_v[r >> 5] = mine ? (eq ? m : 0u) : keep_v[r >> 5];
+              keep_i[r >> 5] = mine ? (eq ? gb_k + __ffs(eq) - 1 : -1) : keep_i[r >> 5];
+#endif
+            }
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int r = lane + 32 * q;
+          if (r < ncol) {
+            sm.part.v[pp][tw][r] = keep_v[q];
+            sm.part.i[pp][tw][r] = keep_i[q];
+          }
+        }
+        if (gi < ncol && gi_valid) sm.diag[pp][gi] = dg;
+      }
+      // the remainder guide token: exact fp32 dot products from the feed warps, softmax by one warp
+      if (n_rem == 1 && tw < n_here) {
+        const int pp = tw;
+        float l[3], mx = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int j = lane + 32 * q;
+          l[q] = j < T ? sm.rem[slot][pp][j] * inv_na_rem * (100.0f * 1.4426950408889634f) : -INFINITY;
+          mx = fmaxf(mx, l[q]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float e[3], s = 0.f;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          e[q] = ex2_approx(l[q] - mx);
+          s += e[q];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float inv = 1.0f / s;
+        float* simrow = a.sim ? a.sim + (static_cast<size_t>(b * KB_NP + pp) * A + a.a_mma) * T : nullptr;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int j = lane + 32 * q;
+          if (j < T) {
+            sm.prem[pp][j] = e[q] * inv;
+            if (simrow) simrow[j] = e[q] * inv;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.acc_free);  // TMEM may be overwritten by the next batch
+      named_bar_sync(1, KB_TAIL_THREADS);
+      if (ttid == 0) KB_STAMP(bl, 2);
+      // ---- 3a. combine the partials: best guide token per column (ties -> lowest index: the partials are in
+      // ascending guide order and only a strictly larger value replaces the current one)
+      for (int idx = ttid; idx < n_here * NPAD; idx += KB_TAIL_THREADS) {
+        const int pp = idx / NPAD, r = idx - pp * NPAD;
+        if (r < ncol) {
+          float bs = -1.f;
+          int bi = -1;
+#pragma unroll
+          for (int w = 0; w < KB_TAIL_WARPS; ++w) {
+            const int i = sm.part.i[pp][w][r];
+            const float sv = __uint_as_float(sm.part.v[pp][w][r]);
+            if (i >= 0 && (bi < 0 || sv > bs)) {
+              bs = sv;
+              bi = i;
+            }
+          }
+          if (n_rem == 1) {
+            const float sv = sm.prem[pp][r + 1];
+            if (bi < 0 || sv > bs) {
+              bs = sv;
+              bi = a.a_mma;
+            }
+          }
+          sm.amax_s[pp][r] = bs;
+          sm.amax_i[pp][r] = bi;
+        }
+      }
+      named_bar_sync(1, KB_TAIL_THREADS);
+      if (ttid == 0) KB_STAMP(bl, 3);
+      // ---- per parameter set: mapping by mode, weights (one warp per prompt), blend
+      for (int p = 0; p < a.n_params; ++p) {
+        const fd_tween_params prm = p < KB_PRM ? sm.prm[p] : a.params[p];
+        for (int idx = ttid; idx < n_here * KB_MT; idx += KB_TAIL_THREADS) {
+          const int pp = idx / KB_MT, r = idx - pp * KB_MT;
+          float ms = 0.f;
+          int mi = 0;
+          if (prm.align_mode == FD_GUIDE_ORDER_DIRECT) {
+            if (r < ncol && r < A) {  // guidance.py:60-69
+              mi = r;
+              ms = (n_rem == 1 && r == a.a_mma) ? sm.prem[pp][r + 1] : sm.diag[pp][r];
+            }
+          } else if (r < ncol) {
+            // guidance.py:57-59,70-84 with reuse; a column whose maximum is exactly 0.0 keeps being
+            // overwritten (Q4) and ends at the last guide token
+            if (sm.amax_s[pp][r] > 0.f) {
+              ms = sm.amax_s[pp][r];
+              mi = sm.amax_i[pp][r];
+            } else {
+              mi = A - 1;
+            }
+          }
+          sm.m.map_s[pp][r] = ms;
+          sm.m.map_idx[pp][r] = mi;
+        }
+        named_bar_sync(1, KB_TAIL_THREADS);
+#ifndef KB_X_SKIP_WEIGHTS
+        if (tw < n_here)
+#else
+        if (false)
+#endif
+        {
+          const int pp = tw;
+          const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
+          const size_t bp = static_cast<size_t>(b * KB_NP + pp) * a.n_params + p;
+          k1_weights_warp(prm, mv, p < KB_PRM ? sm.lin_w[p] : a.lin_w + static_cast<size_t>(p) * T, T, lane, bp, a,
+                          sm.range_flag[slot][pp]);
+        }
+        named_bar_sync(1, KB_TAIL_THREADS);
+        if (ttid == 0 && p == 0) KB_STAMP(bl, 4);
+        for (int pp = 0; pp < n_here; ++pp) {
+          const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
+          const float* text = a.text + static_cast<size_t>(b * KB_NP + pp) * T * D;
+          if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
+            k1_slerp_rows(mv, text, a.guide, T, D, tw, KB_TAIL_WARPS, lane);
+            named_bar_sync(1, KB_TAIL_THREADS);
+          }
+          const size_t bp = static_cast<size_t>(b * KB_NP + pp) * a.n_params + p;
+          k1_blend_rows_warp(mv, text, a.guide, a.out + bp * T * D, T, D, tw, KB_TAIL_WARPS, lane);
+        }
+        named_bar_sync(1, KB_TAIL_THREADS);
+        if (ttid == 0 && p == 0) KB_STAMP(bl, 5);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace
 }  // namespace fd
 
@@ -948,12 +1553,16 @@ extern "C" int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D) {
 
 // development aid (not part of the product ABI): device buffer of >= 8 int64 for phase timestamps
 extern "C" void fd_debug_set_k1_timing(void* buf_dev) { fd::g_k1_timing = static_cast<long long*>(buf_dev); }
+extern "C" void fd_debug_set_k1_fast(int on, int min_prompts) {
+  fd::g_k1_fast = on;
+  if (min_prompts > 0) fd::g_k1_fast_min_prompts = min_prompts;
+}
 
 extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n_text, int guide_batch, int T, int A,
                             int D, const fd_tween_params* params_dev, const float* linear_weights_dev, int n_params,
                             float* out_dev, float* map_s_dev, int32_t* map_idx_dev, float* weights_dev,
                             int32_t* status_dev, float* sim_dev, void* workspace_dev, int64_t workspace_bytes,
-                            void* stream) {
+                            const fd_tween_params* params_host, void* stream) {
   using namespace fd;
   FD_REQUIRE(text_dev && guide_dev && params_dev && linear_weights_dev && out_dev, "fd_sim_blend: NULL pointer");
   FD_REQUIRE(n_text > 0 && n_params > 0, "fd_sim_blend: n_text=%d n_params=%d must be positive", n_text, n_params);
@@ -1029,6 +1638,32 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   a.weights = weights_dev;
   a.status = status_dev;
   a.sim = sim_dev;
+  // ---- batched fast path (K1B): many prompts, one shared guide, mappings with reuse / DIRECT
+  {
+    // the mapping modes decide the kernel, so the fast path needs the host copy of the parameters
+    bool eligible = g_k1_fast && params_host != nullptr && guide_batch == 1 && a_mma > 128 && a_mma <= 256 &&
+                    A - a_mma <= 1 && n_text >= g_k1_fast_min_prompts;
+    for (int q = 0; eligible && q < n_params; ++q)
+      eligible = params_host[q].align_mode == FD_GUIDE_ORDER_DIRECT || params_host[q].mapping_reuse != 0;
+    if (eligible) {
+      CUtensorMap t1, t2;
+      for (int which = 0; which < 2; ++which) {
+        uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), 1};
+        uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(A) * D * 2};
+        uint32_t box[3] = {KC, 256, 1};
+        rc = encode_tmap(which ? &t2 : &t1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                         which ? static_cast<const void*>(g_lo) : g_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc != FD_OK) return rc;
+      }
+      const int sms_b = sm_count();
+      if (sms_b <= 0) return set_error(FD_ERR_CUDA, "fd_sim_blend: cannot query SM count");
+      const int n_batches = (n_text + KB_NP - 1) / KB_NP;
+      FD_CUDA_OK(cudaFuncSetAttribute(k1b_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES));
+      k1b_sim_blend_kernel<<<n_batches < sms_b ? n_batches : sms_b, KB_THREADS, KB_SMEM_BYTES, cst>>>(t1, t2, a);
+      FD_CUDA_OK(cudaGetLastError());
+      return FD_OK;
+    }
+  }
   // enough CTAs to fill the machine: split the parameter sets of one prompt over several CTAs
   // (each redoes the cheap similarity GEMM) when there are few prompts
   const int sms = sm_count();

@@ -178,6 +178,10 @@ int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddi
                  float*   sim_dev,           /* [n_text, A, T] softmax matrix P (debug, or NULL) */
                  void*    workspace_dev,     /* >= fd_sim_blend_workspace_bytes(...) scratch     */
                  int64_t  workspace_bytes,
+                 const fd_tween_params* params_host, /* HOST copy of params_dev, or NULL.  With it the
+                                                library may pick the batched kernel (many prompts, one
+                                                guide, mappings with reuse / DIRECT); results are the
+                                                same either way                                      */
                  void* stream);
 
 /* Scratch needed by fd_sim_blend for the split planes and norms of the guide (an upper bound). */

@@ -7,7 +7,7 @@ from flexdiffuse_b200 import _native
 dev = torch.device('cuda:0')
 lib = _native.lib()
 lib.fd_debug_set_k1_timing.argtypes = [ctypes.c_void_p]
-buf = torch.zeros(8, dtype=torch.int64, device=dev)
+buf = torch.zeros(256, dtype=torch.int64, device=dev)
 for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
     txt = torch.randn(nb, 77, 768, device=dev)
     img = torch.randn(1, 257, 768, device=dev)
@@ -26,3 +26,12 @@ for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
     t = buf.cpu().tolist()
     print(f'prompts={nb} mode={mode} reuse={reuse}: kernel {a.elapsed_time(b)*1e3:.1f} us; '
           f'phases ns {[t[i] - t[0] for i in range(6)]} softmax-internal {[t[6]-t[0], t[7]-t[0]]}')
+    if t[64 + 9]:  # batched kernel: per-batch events of CTA 0, ns from the first MMA commit's batch start
+        t0 = min(x for x in t[64:64 + 16 * 8] if x)
+        for bl in range(8):
+            ev = t[64 + 16 * bl: 64 + 16 * bl + 10]
+            if ev[9]:
+                print('   batch', bl, {k: (ev[i] - t0 if ev[i] else None) for k, i in
+                                       (('feed_done', 8), ('mma_done', 9), ('norms', 0), ('acc', 1), ('drained', 2),
+                                        ('combined', 3), ('weights', 4), ('blend', 5))})
+    buf.zero_()

@@ -5,7 +5,8 @@ product pipeline (bf16 UNet, K2 cache, K3F / K3, fused K4, CUDA graph, K10 tail)
 oracle loop (oracle/loop_oracle.py on oracle/unet_oracle.py, TF32 off) on the same random-init
 weights, same prompt embeddings, same initial noise.
 
-Stated tolerances: final latents relative L2 <= 8e-2; decoded 512x512 images PSNR >= 28 dB
+Stated tolerances: final latents relative L2 <= 3e-2; decoded 512x512 images PSNR >= 38 dB
+(measured on B200: 1.3e-2 and 46.8 dB)
 (50 sequential bf16 UNet evaluations, each amplified 7.5x by CFG; the 10-step 256^2 cases in
 test_pipeline_parity.py hold 5e-2 / 30 dB).'''
 import pytest
@@ -20,8 +21,8 @@ from tests.model_helpers import models, psnr, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-LATENT_TOL = 8e-2
-PSNR_MIN = 28.0
+LATENT_TOL = 3e-2
+PSNR_MIN = 38.0
 
 
 class _Enc:
