@@ -30,7 +30,8 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_kv_project', 'fd_cross_attn', 'fd_cross_attn_fused',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
-               'fd_composite_eps', 'fd_image_tail_u8')
+               'fd_composite_eps', 'fd_image_tail_u8', 'fd_visual_projection',
+               'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag')
 
 
 class NativeError(RuntimeError):
@@ -133,6 +134,11 @@ def lib() -> C.CDLL:
     l.fd_composite_eps.argtypes = [vp, C.c_int, C.POINTER(EntityBox), C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp, vp, vp]
     l.fd_composite_eps.restype = C.c_int
+    l.fd_visual_projection_workspace_bytes.argtypes = [C.c_int, C.c_int]
+    l.fd_visual_projection_workspace_bytes.restype = C.c_int64
+    l.fd_visual_projection.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, vp]
+    l.fd_visual_projection.restype = C.c_int
+    l.fd_visual_projection_range_flag.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -492,3 +498,32 @@ def image_tail_u8(image: torch.Tensor) -> torch.Tensor:
     check(rc, 'fd_image_tail_u8')
     count_launch()
     return out
+
+
+# --------------------------------------------------------------------------- K1P
+_proj_planes = {}
+
+
+def visual_projection(hidden: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    '''fd_visual_projection: hidden [..., K] fp32 @ weight[N, K]^T -> [..., N] fp32 with fp32
+    accuracy on tcgen05.  The split weight planes are cached per (weight storage, version).'''
+    _need(weight, 'weight', torch.float32)
+    if hidden.dtype != torch.float32 or not hidden.is_cuda:
+        raise NativeError('visual_projection needs CUDA float32 hidden states')
+    h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
+    M, K = h2.shape
+    N = weight.shape[0]
+    key = (weight.data_ptr(), weight._version, N, K)
+    ent = _proj_planes.get(weight.device)
+    changed = ent is None or ent[0] != key
+    if changed:
+        ws = torch.empty(lib().fd_visual_projection_workspace_bytes(N, K), dtype=torch.uint8,
+                         device=weight.device)
+        _proj_planes[weight.device] = (key, ws)
+    ws = _proj_planes[weight.device][1]
+    out = torch.empty((M, N), dtype=torch.float32, device=hidden.device)
+    rc = lib().fd_visual_projection(ptr(h2), ptr(weight), ptr(out), M, N, K, ptr(ws), ws.numel(),
+                                    int(changed), stream_ptr(hidden.device))
+    check(rc, 'fd_visual_projection')
+    count_launch(2 if changed else 1)
+    return out.reshape(*hidden.shape[:-1], N)

@@ -187,6 +187,23 @@ int fd_sim_blend(const float* text_dev,      /* [n_text, T, D] fp32 base embeddi
 /* Scratch needed by fd_sim_blend for the split planes and norms of the guide (an upper bound). */
 int64_t fd_sim_blend_workspace_bytes(int guide_batch, int A, int D);
 
+/* ---- K1P: CLIP visual_projection as the prologue of K1 --------------------------------- *
+ * Replaces encode/clip.py:100  `clip.visual_projection(hidden_states)`  (Linear 1024 -> 768, no
+ * bias, on all 257 post-layernorm vision tokens): out[M,N] = hidden[M,K] . weight[N,K]^T in fp32
+ * accuracy (two-term fp16 split on tcgen05, like K1's similarity GEMM), so the guide embeddings K1
+ * consumes never leave the hand-written path.  The weight planes live in `workspace_dev`; pass
+ * weights_changed != 0 on the first call and whenever the weight tensor changes.             */
+int64_t fd_visual_projection_workspace_bytes(int N, int K);
+int fd_visual_projection(const float* hidden_dev,   /* [M, K] fp32, M = images * 257               */
+                         const float* weight_dev,   /* [N, K] fp32 visual_projection.weight        */
+                         float*       out_dev,      /* [M, N] fp32                                 */
+                         int M, int N, int K,       /* K % 64 == 0, N % 4 == 0                     */
+                         void* workspace_dev, int64_t workspace_bytes, int weights_changed,
+                         void* stream);
+/* 1 if an operand since the last call left the split's range (|activation| >= 1023, |weight| >= 63
+ * or non-finite), clearing the flag; synchronises the device.                                 */
+int fd_visual_projection_range_flag(void);
+
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
  * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'
  * CrossAttention.forward recomputes for each of the 16 attn2 layers at every step,

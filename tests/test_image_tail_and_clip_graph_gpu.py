@@ -72,3 +72,71 @@ def test_clip_towers_graph_replay_equals_eager(native, cuda_dev):
     assert any(g for g in graphed._graphs.values()), 'no tower was captured'
     assert not torch.equal(first, second)           # a replay does not alias the previous result
     assert first.data_ptr() != second.data_ptr()
+
+
+@pytest.mark.parametrize('M,N,K', [(257, 768, 1024), (514, 768, 1024), (100, 64, 128), (129, 260, 192)])
+def test_visual_projection_is_fp32_accurate(native, cuda_dev, M, N, K):
+    '''K1P `fd_visual_projection` (encode/clip.py:100) against a float64 matmul: the two-term fp16
+    split must be as accurate as the fp32 Linear it replaces (stated bar: max error <= 4e-6 of the
+    row scale |h| |w|; torch's own fp32 GEMM sits at ~1e-6 on the same inputs).'''
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        g = torch.Generator(device=cuda_dev).manual_seed(M + N + K)
+        h = torch.randn(M, K, device=cuda_dev, generator=g) * 1.7
+        h[0, :7] = torch.tensor([30.0, -45.0, 1e-4, -1e-5, 0.0, 7.25, 500.0], device=cuda_dev)
+        w = torch.randn(N, K, device=cuda_dev, generator=g) * 0.03
+        got = native.visual_projection(h, w)
+        want = h.double() @ w.double().t()
+        scale = h.double().norm(dim=1, keepdim=True) * w.double().norm(dim=1)[None]
+        err = ((got.double() - want).abs() / scale).max().item()
+        ref_err = (((h @ w.t()).double() - want).abs() / scale).max().item()
+        assert tuple(got.shape) == (M, N)
+        assert err <= 4e-6, (err, ref_err)
+        assert native.lib().fd_visual_projection_range_flag() == 0
+        # batched leading dims, and a changed weight tensor invalidates the cached planes
+        got3 = native.visual_projection(h.view(1, M, K), w * 2)
+        torch.testing.assert_close(got3[0], got * 2, rtol=1e-5, atol=1e-6)
+        # out-of-range activations are flagged, not silently wrong
+        h2 = h.clone()
+        h2[1, 3] = 5000.0
+        native.visual_projection(h2, w * 2)
+        assert native.lib().fd_visual_projection_range_flag() == 1
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_clip_encoder_image_uses_projection_kernel(native, cuda_dev):
+    '''CLIP ViT-L/14 widths (1024 -> 768): CLIPEncoder.image goes through K1P and matches the plain
+    fp32 Linear to 1e-5 of the output scale.'''
+    from transformers import CLIPConfig, CLIPModel
+    from flexdiffuse_b200.encode.clip import CLIPEncoder
+    from tests.encode_helpers import FakeTok, test_images
+    cfg = CLIPConfig(
+        text_config=dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=4,
+                         vocab_size=1000, max_position_embeddings=77),
+        vision_config=dict(hidden_size=1024, intermediate_size=512, num_hidden_layers=1, num_attention_heads=16,
+                           image_size=224, patch_size=14),
+        projection_dim=768)
+    torch.manual_seed(5)
+    clip = CLIPModel(cfg).eval().requires_grad_(False).to(cuda_dev)
+    enc = CLIPEncoder(clip, FakeTok(), cuda_graph=False)
+    img = test_images()[0]
+    before = native.LAUNCHES
+    with torch.no_grad():
+        got = enc.image(img)
+        assert native.LAUNCHES > before
+        # the same tower with the stock Linear
+        from torchvision.transforms.functional import InterpolationMode, center_crop, normalize, resize
+        from flexdiffuse_b200.encode.clip import _CLIP_MEAN, _CLIP_STD, preprocess
+        x = preprocess(img)
+        side = min(x.shape[-2:])
+        x = normalize(resize(center_crop(x, [side, side]), [224, 224], interpolation=InterpolationMode.BICUBIC,
+                             antialias=True), list(_CLIP_MEAN), list(_CLIP_STD)).to(cuda_dev)
+        vm = clip.vision_model
+        hid = vm.encoder(inputs_embeds=vm.pre_layrnorm(vm.embeddings(x)), return_dict=True)[0]
+        want = clip.visual_projection(vm.post_layernorm(hid))
+    assert tuple(got.shape) == (1, 257, 768)
+    # both are fp32-accurate products of the same operands: they differ by rounding-order noise,
+    # ~1e-6 of the output scale (elementwise rtol would be meaningless for outputs near zero)
+    assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
