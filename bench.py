@@ -432,7 +432,7 @@ def kernel_rooflines(dev, unet, peaks):
     return out
 
 
-def guide_embeds_e2e(dev, n=10):
+def guide_embeds_e2e(dev, n=10, tf32=False, clip=None):
     '''`Guide.embeds(prompt, image)` end to end on the GPU (BASELINE.json configs[0] on the B200):
     random-init CLIP ViT-L/14 towers (CUDA-graphed PyTorch) + K1, one prompt x one 512x512 guide
     image, the reference's default Linear + Clustered + Threshold parameters.  Returns calls per
@@ -441,8 +441,8 @@ def guide_embeds_e2e(dev, n=10):
     from PIL import Image
     from flexdiffuse_b200 import factory
     from flexdiffuse_b200.guidance import Guide
-    clip = factory.build_clip(dev)
-    guide = Guide(clip, factory.FakeTokenizer(), device=str(dev))
+    clip = clip if clip is not None else factory.build_clip(dev)
+    guide = Guide(clip, factory.FakeTokenizer(), device=str(dev), tf32_towers=tf32)
     img = Image.fromarray((np.random.RandomState(0).rand(512, 512, 3) * 255).astype('uint8'))
     prompt = 'a photograph of an astronaut riding a horse'
     kw = {}
@@ -459,7 +459,22 @@ def guide_embeds_e2e(dev, n=10):
             out = guide.embeds(prompt, img, **kw)
         torch.cuda.synchronize()
     assert tuple(out.shape) == (1, 77, 768)
-    return n / (time.perf_counter() - t0)
+    rate = n / (time.perf_counter() - t0)
+    with torch.no_grad():
+        gi = guide.encoder.image(img)
+    return rate, gi
+
+
+def _guide_rates(dev):
+    from flexdiffuse_b200 import factory
+    clip = factory.build_clip(dev)
+    r32, g32 = guide_embeds_e2e(dev, clip=clip)
+    rtf, gtf = guide_embeds_e2e(dev, tf32=True, clip=clip)
+    return {'gpu_guide_embeds_calls_per_s': r32,
+            'gpu_guide_embeds_calls_per_s_tf32_towers': rtf,
+            'tf32_towers_image_embedding_rel_l2_vs_fp32': ((gtf - g32).norm() / g32.norm()).item(),
+            'guide_embeds_note': 'fp32 towers (the reference\'s precision) are CUDA-core GEMM bound: 155 GFLOP of '
+                                 'fp32 per image; tf32_towers=True is the opt-in tensor-core variant'}
 
 
 # ------------------------------------------------------------------ plain-torch GPU baseline
@@ -954,7 +969,7 @@ def main():
         line['cpu_baseline'] = base
         cb = cpu_blend_baseline()
         line['blends'] = {'gpu_blends_per_s': kr['k1']['blends_per_s'],
-                          'gpu_guide_embeds_calls_per_s': guide_embeds_e2e(dev),
+                          **_guide_rates(dev),
                           'cpu_blends_per_s': cb, 'cpu_kind': 'port (vectorised oracle; the reference\'s own '
                                                               'Tweener.tween loops: 3-10 blends/s on 8 cores, BASELINE.md section 2)',
                           'cpu_cores': os.cpu_count(),

@@ -188,8 +188,183 @@ k2_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   }
 }
 
+
+// v4: cta_group::2.  One tcgen05.mma spans a PAIR of CTAs: M = 256 (128 context rows in each CTA's shared
+// memory and TMEM) x N = 256, and each CTA holds only HALF of the weight tile (128 of its 256 rows).  What
+// bounds v3 is the bytes an SM has to take in per MMA cycle (A 16 KB + B 32 KB per 512 tensor cycles =
+// 94 B / clk against ~50-64 B / clk an SM ingests, measured in profiles/r02/SUMMARY.md: multicast saves L2 reads,
+// not SM ingest); with the pair sharing B every CTA takes in 16 + 16 KB per 512 cycles = 62 B / clk, and the
+// 32 KB stages allow a 6-deep ring.  Leader CTA (rank 0): arms the stage barrier with both CTAs' bytes and
+// issues the MMAs; both CTAs run their own TMA producer (their A rows + their half of B, signalled on the
+// leader's barrier) and their own epilogue (their 128 rows of the accumulator).
+constexpr int STAGES2 = 5;
+constexpr int K2_THREADS2 = 320;       // TMA, MMA, 8 epilogue warps (two column halves x four lane quarters)
+constexpr int OUT_BUFS2 = 4;           // two staging buffers per epilogue half
+constexpr int B2_STAGE_BYTES = B_STAGE_BYTES / 2;
+constexpr int STAGE2_BYTES = A_STAGE_BYTES + B2_STAGE_BYTES;  // 32768
+constexpr int K2_SMEM2 = STAGES2 * STAGE2_BYTES + OUT_BUFS2 * OUT_CHUNK_BYTES + 1024 /*align*/ + 256 /*bars*/;
+__device__ int g_k2_flag;  // first bounded wait that gave up (0 = none)
+
+__global__ void __launch_bounds__(K2_THREADS2, 1)
+k2_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bh,
+                const __grid_constant__ CUtensorMap tm_out, int M, int N, int K, int m_pairs, int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + STAGES2 * STAGE2_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + OUT_BUFS2 * OUT_CHUNK_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full = empty_bar + STAGES2;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2] (leader's copy is the one that counts: 2 x 8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = K / BK;
+  const int total_tiles = m_pairs * n_tiles;
+  const uint32_t crank = cluster_cta_rank();
+  const bool leader = crank == 0;
+  const int first_tile = static_cast<int>(blockIdx.x >> 1);
+  const int tile_stride = static_cast<int>(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_bh);
+    tma_prefetch_desc(&tm_out);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();  // both CTAs' barriers and TMEM exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const int m_blk = tile % m_pairs, n_blk = tile / m_pairs;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait_bounded(&empty_bar[s], ((it / STAGES2) & 1) ^ 1, &g_k2_flag, 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE2_BYTES);
+          const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[s]), 0);
+          tma_load_2d_2cta(smem + s * STAGE2_BYTES, &tm_a, lead_bar, kb * BK, m_blk * 2 * BM + static_cast<int>(crank) * BM);
+          tma_load_2d_2cta(smem + s * STAGE2_BYTES + A_STAGE_BYTES, &tm_bh, lead_bar, kb * BK,
+                           n_blk * BN + static_cast<int>(crank) * (BN / 2));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 2 * BM, BN, 0, 0);
+      int it = 0, local = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+        const int acc = local & 1;
+        mbar_wait_bounded(&tmem_empty[acc], ((local >> 1) & 1) ^ 1, &g_k2_flag, 2);  // both epilogues drained it
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait_bounded(&full_bar[s], (it / STAGES2) & 1, &g_k2_flag, 3);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * STAGE2_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE2_BYTES + A_STAGE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_f16_ss_2cta(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit_2cta_mcast(&empty_bar[s], 0x3);  // both producers may refill the stage
+        }
+        tc_commit_2cta_mcast(&tmem_full[acc], 0x3);  // both epilogues may read their half
+      }
+    }
+  } else {
+    // 8 epilogue warps: lane quarter = warp % 4 (TMEM access rule), column half = (warp - 2) / 4.  Each half
+    // drains its 128 columns in two 64-column chunks through its own pair of staging buffers, its own named
+    // barrier and its own TMA-store issuer, so the two halves never wait for each other.
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const bool issuer = (threadIdx.x - 64) % 128 == 0;  // first thread of each half
+    uint8_t* my_stage = out_stage + half * 2 * OUT_CHUNK_BYTES;
+    int local = 0, chunk_no = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+      const int m_blk = tile % m_pairs, n_blk = tile / m_pairs;
+      const int acc = local & 1;
+      mbar_wait_bounded(&tmem_full[acc], (local >> 1) & 1, &g_k2_flag, 4);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 64, ++chunk_no) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld_x16(tbase + c0 + 16 * g, v[g]);
+        tmem_ld_wait();
+        uint8_t* buf = my_stage + (chunk_no & 1) * OUT_CHUNK_BYTES;
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1 + half, 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[g][8 * h + 2 * j]),
+                                                       __uint_as_float(v[g][8 * h + 2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&b);
+            }
+            *reinterpret_cast<uint4*>(buf + sw128_offset(row, 2 * g + h)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          tma_store_2d(&tm_out, buf, n_blk * BN + c0, m_blk * 2 * BM + static_cast<int>(crank) * BM);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // on the LEADER's barrier
+    }
+    if (issuer) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();  // no CTA exits (or frees TMEM) while its peer may still signal / multiply into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+int g_k2_variant = 2;  // development aid: 2 = cta_group::2 pairs when M > 128, 1 = v3 (cta_group::1)
+
 }  // namespace
 }  // namespace fd
+
+// development aids: kernel variant, and the bounded-wait record of the cta_group::2 kernel (0 = clean)
+extern "C" void fd_debug_set_k2_variant(int v) { fd::g_k2_variant = v; }
+extern "C" int fd_debug_k2_flag(void) {
+  int v = -1;
+  cudaMemcpyFromSymbol(&v, fd::g_k2_flag, sizeof(int));
+  int z = 0;
+  cudaMemcpyToSymbol(fd::g_k2_flag, &z, sizeof(int));
+  return v;
+}
 
 extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, void* out_bf16_dev,
                              int M, int N, int K, void* stream) {
@@ -244,6 +419,39 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_k2_variant == 2 && m_tiles >= 2 && sms >= 2) {
+    // cta_group::2 path: pairs of CTAs own 256 rows (the last pair may be partly or, for an odd number of
+    // m tiles, half empty: TMA zero-fills and clips)
+    CUtensorMap tm_bh;
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BK, BN / 2};
+    rc = encode_tmap(&tm_bh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_bf16_dev, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+    static thread_local int attr2_device = -1;
+    if (attr2_device != dev) {
+      FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM2));
+      attr2_device = dev;
+    }
+    const int m_pairs = (m_tiles + 1) / 2;
+    const int tiles2 = m_pairs * n_tiles;
+    const int max_pairs = sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles2 < max_pairs ? tiles2 : max_pairs)));
+    cfg.blockDim = dim3(K2_THREADS2);
+    cfg.dynamicSmemBytes = K2_SMEM2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k2_gemm2_kernel, tm_a, tm_bh, tm_out, M, N, K, m_pairs, n_tiles));
+    return FD_OK;
+  }
   if (m_tiles % 2 == 0 && sms >= 2) {
     // paired path: tiles 2q and 2q+1 share their weight tile (m is the fast index and m_tiles is even)
     CUtensorMap tm_bh;  // half-height box of the weight tile: each CTA of a pair loads 128 of the 256 rows

@@ -140,3 +140,20 @@ def test_clip_encoder_image_uses_projection_kernel(native, cuda_dev):
     # both are fp32-accurate products of the same operands: they differ by rounding-order noise,
     # ~1e-6 of the output scale (elementwise rtol would be meaningless for outputs near zero)
     assert (got - want).abs().max().item() <= 1e-5 * want.abs().max().item()
+
+
+def test_tf32_towers_are_opt_in_and_close(native, cuda_dev):
+    '''tf32=True runs the towers' GEMMs in TF32 (stated: embeddings within 5e-3 relative L2 of the
+    fp32 towers); the default stays exact fp32 and leaves the global matmul flag untouched.'''
+    from flexdiffuse_b200.encode.clip import CLIPEncoder
+    from tests.encode_helpers import FakeTok, test_images, tiny_clip
+    clip = tiny_clip().to(cuda_dev)
+    exact = CLIPEncoder(clip, FakeTok(), cuda_graph=False)
+    fast = CLIPEncoder(clip, FakeTok(), tf32=True)
+    flag = torch.backends.cuda.matmul.allow_tf32
+    with torch.no_grad():
+        a, b = exact.image(test_images()[0]), fast.image(test_images()[0])
+        c, d = exact.prompt('a red fox'), fast.prompt('a red fox')
+    assert torch.backends.cuda.matmul.allow_tf32 == flag
+    assert ((a - b).norm() / a.norm()).item() < 5e-3
+    assert ((c - d).norm() / c.norm()).item() < 5e-3
