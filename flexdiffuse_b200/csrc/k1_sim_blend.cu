@@ -1105,9 +1105,11 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = a.T, A = a.A, D = a.D;
   const int num_kc = D / KC;
-  const int n_batches = (a.n_text + KB_NP - 1) / KB_NP;
-  const int my_batches = (n_batches - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
-                         static_cast<int>(gridDim.x);
+  // every CTA takes a contiguous, balanced share of the prompts (shares differ by at most one prompt) and
+  // walks it two prompts at a time; the last batch of a CTA may hold a single prompt
+  const int p_lo = static_cast<int>((static_cast<long long>(a.n_text) * blockIdx.x) / gridDim.x);
+  const int p_hi = static_cast<int>((static_cast<long long>(a.n_text) * (blockIdx.x + 1)) / gridDim.x);
+  const int my_batches = (p_hi - p_lo + KB_NP - 1) / KB_NP;
   const int n_rem = A - a.a_mma;  // 0 or 1 on this path
 
   if (tid == 0) {
@@ -1188,7 +1190,7 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
     float4 gq0 = make_float4(0.f, 0.f, 0.f, 0.f), gq1 = gq0;
     const int total = my_batches * num_kc;
     auto load_chunk = [&](int g) {
-      const int b = static_cast<int>(blockIdx.x) + (g / num_kc) * static_cast<int>(gridDim.x), kc = g % num_kc;
+      const int p0 = p_lo + (g / num_kc) * KB_NP, kc = g % num_kc;
       if (n_rem == 1) {
         gq0 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
         gq1 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC) + 1);
@@ -1197,8 +1199,8 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
       for (int j = 0; j < KB_ITEMS; ++j) {
         const int f = tt + j * KB_FEED_THREADS;
         const int row = f >> 3, pp = row / NPAD, rr = row - pp * NPAD;
-        const int prompt = b * KB_NP + pp;
-        if (f < KB_NTXT * 8 && rr < T && prompt < a.n_text) {
+        const int prompt = p0 + pp;
+        if (f < KB_NTXT * 8 && rr < T && prompt < p_hi) {
           const float4* src = reinterpret_cast<const float4*>(a.text + (static_cast<size_t>(prompt) * T + rr) * D + kc * KC) +
                               2 * (f & 7);
           rb[j][0] = __ldg(src);
@@ -1302,9 +1304,9 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
     }
     named_bar_sync(1, KB_TAIL_THREADS);
     for (int bl = 0; bl < my_batches; ++bl) {
-      const int b = static_cast<int>(blockIdx.x) + bl * static_cast<int>(gridDim.x);
+      const int p0 = p_lo + bl * KB_NP;  // first prompt of this batch
       const int slot = bl & 1;
-      const int n_here = min(KB_NP, a.n_text - b * KB_NP);
+      const int n_here = min(KB_NP, p_hi - p0);
       if (ttid < KB_NP) sm.range_flag[slot ^ 1][ttid] = 0;  // the feed of batch bl + 1 starts from a clean flag
       mbar_wait(&sm.norm_full[slot], (bl >> 1) & 1);
       if (ttid == 0) KB_STAMP(bl, 0);
@@ -1374,12 +1376,13 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         const float inv = 1.0f / (s0 + s1);
         float dg = 0.f;
         unsigned int keep_v[3] = {0u, 0u, 0u};
-        int keep_i[3] = {-1, -1, -1};
-        float* simrow = (a.sim && gi_valid) ? a.sim + (static_cast<size_t>(b * KB_NP + pp) * A + gi) * T : nullptr;
+        unsigned int keep_e[3] = {0u, 0u, 0u};  // lanes holding the maximum (index derived once, after the loop)
+        float* simrow = (a.sim && gi_valid) ? a.sim + (static_cast<size_t>(p0 + pp) * A + gi) * T : nullptr;
         // opaque copies: without them the compiler re-derives lane / guide index from %tid.x for every column
         int lane_k = lane, gi_k = gi, gb_k = gi_base;
         asm volatile("" : "+r"(lane_k), "+r"(gi_k), "+r"(gb_k));
         const unsigned int vmask = gi_valid ? 0xffffffffu : 0u;
+        const unsigned int valid_lanes = __ballot_sync(0xffffffffu, gi_valid);
         uint32_t v3[2][16];
         tmem_ld_x16(tp, v3[0]);
 #pragma unroll
@@ -1398,10 +1401,10 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
               // arg-max over this warp's 32 guide tokens: positive floats order like their bits
               const unsigned int bits = __float_as_uint(pv) & vmask;
               const unsigned int m = __reduce_max_sync(0xffffffffu, bits);
-              const unsigned int eq = __ballot_sync(0xffffffffu, bits == m) & __ballot_sync(0xffffffffu, vmask != 0u);
+              const unsigned int eq = __ballot_sync(0xffffffffu, bits == m) & valid_lanes;
               const bool mine = lane_k == (r & 31);
-              keep_v[r >> 5] = mine ? (eq ? m : 0u) : keep_v[r >> 5];
-              keep_i[r >> 5] = mine ? (eq ? gb_k + __ffs(eq) - 1 : -1) : keep_i[r >> 5];
+              keep_v[r >> 5] = mine ? m : keep_v[r >> 5];
+              keep_e[r >> 5] = mine ? eq : keep_e[r >> 5];
 #endif
             }
           }
@@ -1410,8 +1413,8 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         for (int q = 0; q < 3; ++q) {
           const int r = lane + 32 * q;
           if (r < ncol) {
-            sm.part.v[pp][tw][r] = keep_v[q];
-            sm.part.i[pp][tw][r] = keep_i[q];
+            sm.part.v[pp][tw][r] = keep_e[q] ? keep_v[q] : 0u;
+            sm.part.i[pp][tw][r] = keep_e[q] ? gb_k + __ffs(keep_e[q]) - 1 : -1;
           }
         }
         if (gi < ncol && gi_valid) sm.diag[pp][gi] = dg;
@@ -1437,7 +1440,7 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         const float inv = 1.0f / s;
-        float* simrow = a.sim ? a.sim + (static_cast<size_t>(b * KB_NP + pp) * A + a.a_mma) * T : nullptr;
+        float* simrow = a.sim ? a.sim + (static_cast<size_t>(p0 + pp) * A + a.a_mma) * T : nullptr;
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
           const int j = lane + 32 * q;
@@ -1515,7 +1518,7 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         {
           const int pp = tw;
           const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
-          const size_t bp = static_cast<size_t>(b * KB_NP + pp) * a.n_params + p;
+          const size_t bp = static_cast<size_t>(p0 + pp) * a.n_params + p;
           k1_weights_warp(prm, mv, p < KB_PRM ? sm.lin_w[p] : a.lin_w + static_cast<size_t>(p) * T, T, lane, bp, a,
                           sm.range_flag[slot][pp]);
         }
@@ -1523,12 +1526,12 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         if (ttid == 0 && p == 0) KB_STAMP(bl, 4);
         for (int pp = 0; pp < n_here; ++pp) {
           const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
-          const float* text = a.text + static_cast<size_t>(b * KB_NP + pp) * T * D;
+          const float* text = a.text + static_cast<size_t>(p0 + pp) * T * D;
           if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
             k1_slerp_rows(mv, text, a.guide, T, D, tw, KB_TAIL_WARPS, lane);
             named_bar_sync(1, KB_TAIL_THREADS);
           }
-          const size_t bp = static_cast<size_t>(b * KB_NP + pp) * a.n_params + p;
+          const size_t bp = static_cast<size_t>(p0 + pp) * a.n_params + p;
           k1_blend_rows_warp(mv, text, a.guide, a.out + bp * T * D, T, D, tw, KB_TAIL_WARPS, lane);
         }
         named_bar_sync(1, KB_TAIL_THREADS);
@@ -1657,7 +1660,7 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
       }
       const int sms_b = sm_count();
       if (sms_b <= 0) return set_error(FD_ERR_CUDA, "fd_sim_blend: cannot query SM count");
-      const int n_batches = (n_text + KB_NP - 1) / KB_NP;
+      const int n_batches = (n_text + KB_NP - 1) / KB_NP;  // fewer CTAs than SMs only when a CTA would hold < 2 prompts
       FD_CUDA_OK(cudaFuncSetAttribute(k1b_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES));
       k1b_sim_blend_kernel<<<n_batches < sms_b ? n_batches : sms_b, KB_THREADS, KB_SMEM_BYTES, cst>>>(t1, t2, a);
       FD_CUDA_OK(cudaGetLastError());
