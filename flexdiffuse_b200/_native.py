@@ -241,15 +241,22 @@ def cfg_sched_step(eps_uncond: Optional[torch.Tensor],
 
 
 # --------------------------------------------------------------------------- K1
+_k1_params = {}      # (device, parameter bytes) -> device copy of the fd_tween_params array
+_k1_workspace = {}   # device -> grow-only scratch for the guide's split planes
+
+
 def sim_blend(text: torch.Tensor,
               guide: torch.Tensor,
               params: Sequence[TweenParams],
               linear_weights: torch.Tensor,
-              want_sim: bool = False):
+              want_sim: bool = False,
+              want_maps: bool = True):
     '''fd_sim_blend.  text [B,T,D] f32, guide [G,A,D] f32 (G in {1,B}),
     linear_weights [P,T] f32 on the same device.
     Returns dict(out [B,P,T,D], map_s [B,P,T], map_idx [B,P,T], weights [B,P,T],
-    status [B,P], sim [B,A,T] | None).'''
+    status [B,P], sim [B,A,T] | None); the three map tensors are None with want_maps=False.
+    Host cost per call: the output allocations only -- the parameter array is uploaded once per
+    distinct value (pinned, cached) and the workspace is a grow-only per-device buffer.'''
     _need(text, 'text', torch.float32)
     _need(guide, 'guide', torch.float32)
     _need(linear_weights, 'linear_weights', torch.float32)
@@ -263,22 +270,34 @@ def sim_blend(text: torch.Tensor,
         raise NativeError(f'linear_weights must be [{P},{T}]')
     dev = text.device
     out = torch.empty((B, P, T, D), dtype=torch.float32, device=dev)
-    map_s = torch.empty((B, P, T), dtype=torch.float32, device=dev)
-    map_idx = torch.empty((B, P, T), dtype=torch.int32, device=dev)
-    weights = torch.empty((B, P, T), dtype=torch.float32, device=dev)
     status = torch.empty((B, P), dtype=torch.int32, device=dev)
+    map_s = map_idx = weights = None
+    if want_maps:
+        map_s = torch.empty((B, P, T), dtype=torch.float32, device=dev)
+        map_idx = torch.empty((B, P, T), dtype=torch.int32, device=dev)
+        weights = torch.empty((B, P, T), dtype=torch.float32, device=dev)
     sim = (torch.empty((B, A, T), dtype=torch.float32, device=dev)
            if want_sim else None)
     arr = (TweenParams * P)(*params)
-    params_dev = torch.frombuffer(bytearray(bytes(arr)),
-                                  dtype=torch.uint8).to(dev)
+    raw = bytes(arr)
+    key = (dev, raw)
+    params_dev = _k1_params.get(key)
+    if params_dev is None:
+        if len(_k1_params) > 512:
+            _k1_params.clear()
+        host = torch.frombuffer(bytearray(raw), dtype=torch.uint8).pin_memory()
+        params_dev = host.to(dev, non_blocking=True)
+        _k1_params[key] = params_dev
     ws_bytes = lib().fd_sim_blend_workspace_bytes(G, A, D)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _k1_workspace.get(dev)
+    if ws is None or ws.numel() < ws_bytes:
+        ws = torch.empty(max(ws_bytes, 1 << 22), dtype=torch.uint8, device=dev)
+        _k1_workspace[dev] = ws
     rc = lib().fd_sim_blend(ptr(text), ptr(guide), B, G, T, A, D,
                             ptr(params_dev),
                             ptr(linear_weights), P, ptr(out), ptr(map_s),
                             ptr(map_idx), ptr(weights), ptr(status), ptr(sim),
-                            ptr(ws), ws_bytes, C.cast(arr, C.c_void_p), stream_ptr(dev))
+                            ptr(ws), ws.numel(), C.cast(arr, C.c_void_p), stream_ptr(dev))
     count_launch()  # guide prep kernel
     check(rc, 'fd_sim_blend')
     count_launch()

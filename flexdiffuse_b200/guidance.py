@@ -123,7 +123,7 @@ class Tweener():
         base = _as_f32_3d(base_emb, 'base_emb')
         alt = _as_f32_3d(alt_emb, 'alt_emb')
         lin = self._linear(base.shape[1], base.device)[None]
-        res = _native.sim_blend(base, alt, [self._params()], lin)
+        res = _native.sim_blend(base, alt, [self._params()], lin, want_maps=VERBOSE)
         if check or VERBOSE:
             status = res['status'].cpu()
             if VERBOSE:
