@@ -525,7 +525,8 @@ _proj_planes = {}
 
 def visual_projection(hidden: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
     '''fd_visual_projection: hidden [..., K] fp32 @ weight[N, K]^T -> [..., N] fp32 with fp32
-    accuracy on tcgen05.  The split weight planes are cached per (weight storage, version).'''
+    accuracy on tcgen05.  The split weight planes are cached per (weight storage, version);
+    the cache holds a reference to the weight.'''
     _need(weight, 'weight', torch.float32)
     if hidden.dtype != torch.float32 or not hidden.is_cuda:
         raise NativeError('visual_projection needs CUDA float32 hidden states')
@@ -538,7 +539,10 @@ def visual_projection(hidden: torch.Tensor, weight: torch.Tensor) -> torch.Tenso
     if changed:
         ws = torch.empty(lib().fd_visual_projection_workspace_bytes(N, K), dtype=torch.uint8,
                          device=weight.device)
-        _proj_planes[weight.device] = (key, ws)
+        # the entry keeps the weight tensor alive: its address cannot be handed to another tensor while
+        # the planes made from it are cached (a freed weight's address coming back with version 0 and
+        # the same shape would otherwise hit the cache with stale planes)
+        _proj_planes[weight.device] = (key, ws, weight)
     ws = _proj_planes[weight.device][1]
     out = torch.empty((M, N), dtype=torch.float32, device=hidden.device)
     rc = lib().fd_visual_projection(ptr(h2), ptr(weight), ptr(out), M, N, K, ptr(ws), ws.numel(),

@@ -1035,38 +1035,61 @@ k1_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_cons
 //     the [T][A] logits matrix, its transposition through shared memory and the four passes over it
 //     are gone.  Column arg-max over the guide tokens = one redux.sync.max.u32 on the float bits + one
 //     ballot per column per warp, then 8 partials per column.
-//   * persistent CTAs (one per SM, 512 threads) with dedicated roles, so the HBM-bound blend of batch b
-//     runs under the GEMM of batch b + 1:  warp 0 TMA (guide planes, 2-stage ring), warp 1 MMA issuer,
-//     warps 2-7 text feed (fp32 -> two fp16 planes, norms, the 257th guide token in exact fp32),
-//     warps 8-15 tail (TMEM drain + softmax + arg-max partials, weights, blend).
+//   * persistent CTAs (one per SM, 512 threads) with dedicated roles and NO thread ever waiting on a
+//     global load (v2; in v1 the feed warps loaded the text into registers one chunk ahead and the tail
+//     warps blended row by row out of registers: both sat on HBM / L2 latency, ~47 us per batch each):
+//       warp 0      TMA producer: guide planes (2-stage ring) and the RAW fp32 text (4-stage ring of
+//                   [160 rows x 32 floats]), K chunks of 32
+//       warp 1      MMA issuer (kind::f16, M128 N160 K16, SWIZZLE_64B operands)
+//       warps 2-5   text feed: raw fp32 chunk (shared memory) -> two fp16 planes, norms, the 257th guide
+//                   token in exact fp32
+//       warps 6-7   blend: rows claimed one at a time from a shared counter; text row + mapped guide row
+//                   straight from L2 into registers (12 x 16 B in flight per lane), 128-bit streaming stores
+//       warps 8-15  tail: TMEM drain + softmax + arg-max partials, mapping, weights -> a double-buffered
+//                   decision table; until the next accumulator is complete they claim blend rows too
+//     The kernel is bound by SHARED-MEMORY bandwidth (SS-mode MMAs at N = 160 read 9 KB per 80 cycles = 115 of
+//     the SM's 128 B/clk on their own; profiles/r02/SUMMARY.md), so nothing but the operands goes through shared
+//     memory: a cp.async / bulk-copy staged blend measured slower than the register one.
 // Everything the fast path cannot do (per-prompt guides, no-reuse greedy mappings, A <= 128 or > 264,
-// more than one remainder row, few prompts) stays on the kernel above.
+// more than one remainder row, D > 1024, few prompts) stays on the kernel above.
 constexpr int KB_THREADS = 512;
-constexpr int KB_FEED_WARPS = 6;
-constexpr int KB_FEED_THREADS = KB_FEED_WARPS * 32;       // 192
+constexpr int KB_FEED_WARPS = 4;
+constexpr int KB_FEED_THREADS = KB_FEED_WARPS * 32;       // 128
+constexpr int KB_BLEND_WARPS = 2;
+constexpr int KB_TAIL_WARP0 = 2 + KB_FEED_WARPS + KB_BLEND_WARPS;  // 8
 constexpr int KB_TAIL_WARPS = 8;
 constexpr int KB_TAIL_THREADS = KB_TAIL_WARPS * 32;       // 256
 constexpr int KB_NP = 2;                                  // prompts per batch
 constexpr int KB_NTXT = KB_NP * NPAD;                     // 160 = UMMA N
-constexpr int KB_G_PLANE = 256 * 128;                     // guide plane of a K chunk: 256 rows x 128 B
-constexpr int KB_T_PLANE = KB_NTXT * 128;                 // text plane: 160 rows x 128 B
-constexpr int KB_STAGE = 2 * KB_G_PLANE + 2 * KB_T_PLANE; // 106496
-constexpr int KB_STAGES = 2;
-constexpr int KB_ITEMS = (KB_NTXT * 8 + KB_FEED_THREADS - 1) / KB_FEED_THREADS;  // 7
+constexpr int KB_KC = 32;                                 // K elements per chunk: 64 B of fp16, 128 B of fp32
+constexpr int KB_G_PLANE = 256 * 64;                      // guide plane of a K chunk: 256 rows x 64 B (SWIZZLE_64B)
+constexpr int KB_T_PLANE = KB_NTXT * 64;                  // text plane: 160 rows x 64 B
+constexpr int KB_PSTAGE = 2 * KB_G_PLANE + 2 * KB_T_PLANE;  // 53248
+constexpr int KB_PSTAGES = 2;
+constexpr int KB_RAW_PROMPT = NPAD * KB_KC * 4;           // 80 rows x 128 B of raw text
+constexpr int KB_RSTAGE = KB_NP * KB_RAW_PROMPT;          // 20480
+constexpr int KB_RSTAGES = 4;
+constexpr int KB_ITEMS = KB_NTXT * 4 / KB_FEED_THREADS;   // 5 items of 8 floats per feed thread and chunk
+static_assert(KB_ITEMS * KB_FEED_THREADS == KB_NTXT * 4, "feed items");
+constexpr int KB_MAX_D = 4096;
 constexpr int KB_MT = MAXT + 16;
 constexpr int KB_PRM = 2;                                 // parameter sets cached in shared memory
 // development aid (fd_debug_set_k1_timing, buffer of >= 256 int64): CTA 0 stamps %globaltimer at
 // [64 + 16 b + e] for its first 8 batches: e = 0 tail sees norms, 1 accumulator complete, 2 TMEM drained,
-// 3 arg-max combined, 4 weights done, 5 blend done; 8 feed finished the batch; 9 MMA committed it
+// 3 arg-max combined, 4 weights done (decisions handed to the blend warps), 5 blend done; 8 feed finished the
+// batch; 9 MMA committed it
 #define KB_STAMP(bl, e)                                                                              \
   do {                                                                                               \
-    if (a.timing && blockIdx.x == 0 && (bl) < 8) a.timing[64 + 16 * (bl) + (e)] = k1_gtime();        \
+    if (a.timing && blockIdx.x == 0 && (bl) < 4) a.timing[64 + 16 * (bl) + (e)] = k1_gtime();        \
+  } while (0)
+// chunk-level stamps of CTA 0's second batch, [128 + 6 c + e] for its first 16 chunks: e = 0 guide planes requested,
+// 1 feed sees the raw chunk, 2 raw chunk requested, 3 feed done, 4 MMA sees the stage full, 5 MMA issued
+#define KB_CSTAMP(g, e)                                                                              \
+  do {                                                                                               \
+    if (a.timing && blockIdx.x == 0 && (g) >= num_kc && (g) < num_kc + 16)                           \
+      a.timing[128 + 6 * ((g) - num_kc) + (e)] = k1_gtime();                                         \
   } while (0)
 
-struct KbPartials {
-  unsigned int v[KB_NP][KB_TAIL_WARPS][NPAD];  // per-warp column maxima (float bits)
-  int i[KB_NP][KB_TAIL_WARPS][NPAD];
-};
 struct KbMaps {
   float map_s[KB_NP][KB_MT];
   int map_idx[KB_NP][KB_MT];
@@ -1081,30 +1104,124 @@ struct KbSmem {
   float diag[KB_NP][NPAD];            // P[r, r + 1] (DIRECT order)
   float amax_s[KB_NP][KB_MT];         // arg-max over the guide tokens per column
   int amax_i[KB_NP][KB_MT];
-  // the arg-max partials die when amax_* is written; the mapping / weight state is born after that
-  union {
-    KbPartials part;
-    KbMaps m;
-  };
+  unsigned int part_v[KB_NP][KB_TAIL_WARPS][NPAD];  // per-warp column maxima (float bits)
+  int part_i[KB_NP][KB_TAIL_WARPS][NPAD];
+  KbMaps m[2];                        // decision tables: written by the tail warps, read by the blend warps
   fd_tween_params prm[KB_PRM];        // the first parameter sets and their linspace rows, loaded once
   float lin_w[KB_PRM][KB_MT];
   int range_flag[2][KB_NP];
-  uint64_t full_bar[KB_STAGES], empty_bar[KB_STAGES], acc_full, acc_free, norm_full[2];
+  uint64_t pfull[KB_PSTAGES], pempty[KB_PSTAGES], rfull[KB_RSTAGES], rempty[KB_RSTAGES];
+  uint64_t acc_full, acc_free, norm_full[2], maps_full[2], last_full;
+  int row_next[4], rows_done[4];      // [unit & 3] rows of a decision table claimed / finished (work stealing)
   uint32_t tmem_slot;
 };
-constexpr int KB_SMEM_BYTES = 1024 + KB_STAGES * KB_STAGE + sizeof(KbSmem);
+constexpr int KB_ARENA = KB_PSTAGES * KB_PSTAGE + KB_RSTAGES * KB_RSTAGE;
+constexpr int KB_SMEM_BYTES = 1024 + KB_ARENA + sizeof(KbSmem);
 static_assert(KB_SMEM_BYTES <= 227 * 1024, "K1B shared memory");
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+__device__ __forceinline__ float4 ldg_nc128(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// one blended row, straight from global memory (both rows are L2 hits: the text row was streamed by the feed a batch
+// ago, the guide is shared by every prompt): SEL 0 = text, 1 = guide, 2 = lerp, 3 = slerp.  NQ float4 per lane
+// (lanes interleaved), all 2 NQ loads in flight before the first use, 128-bit streaming stores.
+template <int SEL, int NQ>
+__device__ __forceinline__ void kb_blend_row(const float4* tp, const float4* gp, float4* op, float w, float ca, float cb) {
+  float4 bv[NQ], av[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    if (SEL != 1) bv[q] = ldg_nc128(tp + 32 * q);
+    if (SEL != 0) av[q] = ldg_nc128(gp + 32 * q);
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    float4 o;
+    if (SEL == 0) {
+      o = bv[q];
+    } else if (SEL == 1) {
+      o = av[q];
+    } else if (SEL == 3) {
+      o.x = __fadd_rn(__fmul_rn(ca, bv[q].x), __fmul_rn(cb, av[q].x));
+      o.y = __fadd_rn(__fmul_rn(ca, bv[q].y), __fmul_rn(cb, av[q].y));
+      o.z = __fadd_rn(__fmul_rn(ca, bv[q].z), __fmul_rn(cb, av[q].z));
+      o.w = __fadd_rn(__fmul_rn(ca, bv[q].w), __fmul_rn(cb, av[q].w));
+    } else {
+      // base + (alt - base) * iw, every op rounded separately like the torch expression
+      o.x = __fadd_rn(bv[q].x, __fmul_rn(__fsub_rn(av[q].x, bv[q].x), w));
+      o.y = __fadd_rn(bv[q].y, __fmul_rn(__fsub_rn(av[q].y, bv[q].y), w));
+      o.z = __fadd_rn(bv[q].z, __fmul_rn(__fsub_rn(av[q].z, bv[q].z), w));
+      o.w = __fadd_rn(bv[q].w, __fmul_rn(__fsub_rn(av[q].w, bv[q].w), w));
+    }
+    __stcs(op + 32 * q, o);
+  }
+}
+template <int NQ>
+__device__ __forceinline__ void kb_blend_row_sel(int sel, const float4* tp, const float4* gp, float4* op, float w,
+                                                 float ca, float cb) {
+  if (sel == 2) kb_blend_row<2, NQ>(tp, gp, op, w, ca, cb);
+  else if (sel == 0) kb_blend_row<0, NQ>(tp, gp, op, w, ca, cb);
+  else if (sel == 1) kb_blend_row<1, NQ>(tp, gp, op, w, ca, cb);
+  else kb_blend_row<3, NQ>(tp, gp, op, w, ca, cb);
+}
+
+// Blend rows of one decision table until none is left to claim.  Rows are claimed one at a time from a shared
+// counter, so the two dedicated blend warps and the tail warps (between two TMEM drains) share the work whatever
+// their timing.  text0 / out0: first prompt of the batch (prompt strides T D and out_pstride floats).
+__device__ __forceinline__ void kb_blend_steal(const KbMaps& mp, int* row_next, int* rows_done, int n_rows, int T, int D,
+                                               const float* text0, const float* guide, float* out0, size_t out_pstride,
+                                               int lane) {
+  const int d4 = D / 4;
+  while (true) {
+    int i = 0;
+    if (lane == 0) i = atomicAdd(row_next, 1);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= n_rows) {
+      if (lane == 0) atomicAdd(rows_done, 1);  // exit token: this warp will not touch the counters of this table again
+      break;
+    }
+    const int pp = i >= T ? 1 : 0, r = i - pp * T;
+    const int sel = mp.sel[pp][r];
+    const float w = mp.iw[pp][r];
+    const float ca = sel == 3 ? mp.slerp_a[pp][r] : 0.f, cb = sel == 3 ? mp.slerp_b[pp][r] : 0.f;
+    const float4* tp = reinterpret_cast<const float4*>(text0 + (static_cast<size_t>(pp) * T + r) * D) + lane;
+    const float4* gp = reinterpret_cast<const float4*>(guide + static_cast<size_t>(mp.map_idx[pp][r]) * D) + lane;
+    float4* op = reinterpret_cast<float4*>(out0 + pp * out_pstride + static_cast<size_t>(r) * D) + lane;
+#ifndef KB_X_SKIP_BLEND
+    if (d4 == 192) {  // D = 768: six float4 per lane, no guards
+      kb_blend_row_sel<6>(sel, tp, gp, op, w, ca, cb);
+    } else {
+      int c = lane;
+      for (; c + 96 < d4; c += 128) kb_blend_row_sel<4>(sel, tp + (c - lane), gp + (c - lane), op + (c - lane), w, ca, cb);
+      for (; c < d4; c += 32) kb_blend_row_sel<1>(sel, tp + (c - lane), gp + (c - lane), op + (c - lane), w, ca, cb);
+    }
+#endif
+    __syncwarp();
+    if (lane == 0) atomicAdd(rows_done, 1);  // the row's decision entries have been read
+  }
+}
 
 __global__ void __launch_bounds__(KB_THREADS, 1)
 k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_h2,
-                     const K1Args a) {
+                     const __grid_constant__ CUtensorMap tm_txt, const K1Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                               ~static_cast<uintptr_t>(1023));
-  KbSmem& sm = *reinterpret_cast<KbSmem*>(stage + KB_STAGES * KB_STAGE);
+  uint8_t* raw = stage + KB_PSTAGES * KB_PSTAGE;
+  KbSmem& sm = *reinterpret_cast<KbSmem*>(stage + KB_ARENA);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int T = a.T, A = a.A, D = a.D;
-  const int num_kc = D / KC;
+  const int num_kc = D / KB_KC;
   // every CTA takes a contiguous, balanced share of the prompts (shares differ by at most one prompt) and
   // walks it two prompts at a time; the last batch of a CTA may hold a single prompt
   const int p_lo = static_cast<int>((static_cast<long long>(a.n_text) * blockIdx.x) / gridDim.x);
@@ -1115,14 +1232,23 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
   if (tid == 0) {
     tma_prefetch_desc(&tm_h1);
     tma_prefetch_desc(&tm_h2);
-    for (int st = 0; st < KB_STAGES; ++st) {
-      mbar_init(&sm.full_bar[st], 1 + KB_FEED_WARPS);
-      mbar_init(&sm.empty_bar[st], 1);
+    tma_prefetch_desc(&tm_txt);
+    for (int st = 0; st < KB_PSTAGES; ++st) {
+      mbar_init(&sm.pfull[st], 1 + KB_FEED_WARPS);
+      mbar_init(&sm.pempty[st], 1);
+    }
+    for (int st = 0; st < KB_RSTAGES; ++st) {
+      mbar_init(&sm.rfull[st], 1);
+      mbar_init(&sm.rempty[st], KB_FEED_WARPS);
     }
     mbar_init(&sm.acc_full, 1);
     mbar_init(&sm.acc_free, KB_TAIL_WARPS);
-    mbar_init(&sm.norm_full[0], KB_FEED_WARPS);
-    mbar_init(&sm.norm_full[1], KB_FEED_WARPS);
+    for (int q = 0; q < 2; ++q) {
+      mbar_init(&sm.norm_full[q], KB_FEED_WARPS);
+      mbar_init(&sm.maps_full[q], 1);
+    }
+    mbar_init(&sm.last_full, 1);
+    for (int q = 0; q < 4; ++q) sm.row_next[q] = sm.rows_done[q] = 0;
     for (int q = 0; q < 2 * KB_NP; ++q) (&sm.range_flag[0][0])[q] = 0;
     fence_mbar_init();
   }
@@ -1136,16 +1262,29 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
   const uint32_t tmem_base = sm.tmem_slot;
 
   if (warp == 0) {
-    // ================================================================ TMA producer: guide planes
-    if (elect_one()) {
-      const int total = my_batches * num_kc;
+    // ================================================================ TMA producers: lane 0 streams the guide planes,
+    // lane 1 the raw text (its ring runs up to RSTAGES chunks ahead of the planes it turns into, independent of the
+    // MMA's progress: the text is the only operand that comes from HBM)
+    const int total = my_batches * num_kc;
+    if (lane == 1) {
       for (int g = 0; g < total; ++g) {
-        const int st = g % KB_STAGES, kc = g % num_kc;
-        mbar_wait_backoff(&sm.empty_bar[st], ((g / KB_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&sm.full_bar[st], 2u * KB_G_PLANE);
-        uint8_t* base = stage + st * KB_STAGE;
-        tma_load_3d(base, &tm_h1, &sm.full_bar[st], kc * KC, 0, 0);
-        tma_load_3d(base + KB_G_PLANE, &tm_h2, &sm.full_bar[st], kc * KC, 0, 0);
+        const int rs = g % KB_RSTAGES, kc = g % num_kc, p0 = p_lo + (g / num_kc) * KB_NP;
+        const int n_here = min(KB_NP, p_hi - p0);
+        mbar_wait_backoff(&sm.rempty[rs], ((g / KB_RSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&sm.rfull[rs], static_cast<uint32_t>(n_here) * KB_RAW_PROMPT);
+        KB_CSTAMP(g, 2);
+        for (int pp = 0; pp < n_here; ++pp)
+          tma_load_3d(raw + rs * KB_RSTAGE + pp * KB_RAW_PROMPT, &tm_txt, &sm.rfull[rs], kc * KB_KC, 0, p0 + pp);
+      }
+    } else if (lane == 0) {
+      for (int g = 0; g < total; ++g) {
+        const int st = g % KB_PSTAGES, kc = g % num_kc;
+        mbar_wait_backoff(&sm.pempty[st], ((g / KB_PSTAGES) & 1) ^ 1);
+        mbar_expect_tx(&sm.pfull[st], 2u * KB_G_PLANE);
+        KB_CSTAMP(g, 0);
+        uint8_t* base = stage + st * KB_PSTAGE;
+        tma_load_3d(base, &tm_h1, &sm.pfull[st], kc * KB_KC, 0, 0);
+        tma_load_3d(base + KB_G_PLANE, &tm_h2, &sm.pfull[st], kc * KB_KC, 0, 0);
       }
     }
   } else if (warp == 1) {
@@ -1157,125 +1296,149 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         if (b > 0) mbar_wait_backoff(&sm.acc_free, (b - 1) & 1);  // the tail has drained batch b - 1
         tc_fence_after();
         for (int kc = 0; kc < num_kc; ++kc, ++g) {
-          const int st = g % KB_STAGES;
-          mbar_wait_backoff(&sm.full_bar[st], (g / KB_STAGES) & 1);
+          const int st = g % KB_PSTAGES;
+          mbar_wait_backoff(&sm.pfull[st], (g / KB_PSTAGES) & 1);
           tc_fence_after();
-          const uint32_t base = smem_u32(stage + st * KB_STAGE);
-          const uint64_t th1 = umma_desc_sw128(base + 2 * KB_G_PLANE, 16, 1024);
-          const uint64_t th2 = umma_desc_sw128(base + 2 * KB_G_PLANE + KB_T_PLANE, 16, 1024);
+          KB_CSTAMP(g, 4);
+          const uint32_t base = smem_u32(stage + st * KB_PSTAGE);
+          const uint64_t th1 = umma_desc_sw64(base + 2 * KB_G_PLANE, 16, 512);
+          const uint64_t th2 = umma_desc_sw64(base + 2 * KB_G_PLANE + KB_T_PLANE, 16, 512);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            const uint64_t gh1 = umma_desc_sw128(base + t * 128 * 128, 16, 1024);
-            const uint64_t gh2 = umma_desc_sw128(base + KB_G_PLANE + t * 128 * 128, 16, 1024);
+            const uint64_t gh1 = umma_desc_sw64(base + t * 128 * 64, 16, 512);
+            const uint64_t gh2 = umma_desc_sw64(base + KB_G_PLANE + t * 128 * 64, 16, 512);
             const uint32_t d = tmem_base + t * KB_NTXT;
 #pragma unroll
-            for (int ks = 0; ks < KC / 16; ++ks) {  // small terms first
+            for (int ks = 0; ks < KB_KC / 16; ++ks) {  // small terms first
               mma_f16_ss(d, gh2 + 2 * ks, th1 + 2 * ks, idesc, (kc | ks) != 0);
               mma_f16_ss(d, gh1 + 2 * ks, th2 + 2 * ks, idesc, 1);
               mma_f16_ss(d, gh1 + 2 * ks, th1 + 2 * ks, idesc, 1);
             }
           }
-          tc_commit(&sm.empty_bar[st]);
+          tc_commit(&sm.pempty[st]);
+          KB_CSTAMP(g, 5);
+          if (a.timing && blockIdx.x == 0 && g >= num_kc + 16 && g < num_kc + 20) {
+            // development aid: isolated latency of one chunk's MMAs (issue end -> commit visible)
+            a.timing[224 + 2 * (g - num_kc - 16)] = k1_gtime();
+            mbar_wait(&sm.pempty[st], (g / KB_PSTAGES) & 1);
+            a.timing[225 + 2 * (g - num_kc - 16)] = k1_gtime();
+          }
         }
         tc_commit(&sm.acc_full);
         KB_STAMP(b, 9);
       }
     }
   } else if (warp < 2 + KB_FEED_WARPS) {
-    // ================================================================ text feed
+    // ================================================================ text feed: raw chunk -> fp16 planes
     const int tt = tid - 64;
-    float4 rb[KB_ITEMS][2];
     float ssb[KB_ITEMS], racc[KB_ITEMS];
-    const float* grem = a.guide + static_cast<size_t>(a.a_mma) * D + (tt & 7) * 8;
+    const float* grem = a.guide + static_cast<size_t>(a.a_mma) * D + (tt & 3) * 8;
     float4 gq0 = make_float4(0.f, 0.f, 0.f, 0.f), gq1 = gq0;
     const int total = my_batches * num_kc;
-    auto load_chunk = [&](int g) {
-      const int p0 = p_lo + (g / num_kc) * KB_NP, kc = g % num_kc;
-      if (n_rem == 1) {
-        gq0 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC));
-        gq1 = __ldg(reinterpret_cast<const float4*>(grem + kc * KC) + 1);
-      }
-#pragma unroll
-      for (int j = 0; j < KB_ITEMS; ++j) {
-        const int f = tt + j * KB_FEED_THREADS;
-        const int row = f >> 3, pp = row / NPAD, rr = row - pp * NPAD;
-        const int prompt = p0 + pp;
-        if (f < KB_NTXT * 8 && rr < T && prompt < p_hi) {
-          const float4* src = reinterpret_cast<const float4*>(a.text + (static_cast<size_t>(prompt) * T + rr) * D + kc * KC) +
-                              2 * (f & 7);
-          rb[j][0] = __ldg(src);
-          rb[j][1] = __ldg(src + 1);
-        } else {
-          rb[j][0] = rb[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    };
-    if (total > 0) load_chunk(0);
+    if (n_rem == 1 && total > 0) {
+      gq0 = __ldg(reinterpret_cast<const float4*>(grem));
+      gq1 = __ldg(reinterpret_cast<const float4*>(grem) + 1);
+    }
     bool oor0 = false, oor1 = false;
     for (int g = 0; g < total; ++g) {
-      const int st = g % KB_STAGES, kc = g % num_kc, bl = g / num_kc;
+      const int st = g % KB_PSTAGES, rs = g % KB_RSTAGES, kc = g % num_kc, bl = g / num_kc;
+      const int n_here = min(KB_NP, p_hi - (p_lo + bl * KB_NP));
       if (kc == 0) {
 #pragma unroll
         for (int j = 0; j < KB_ITEMS; ++j) ssb[j] = racc[j] = 0.f;
         oor0 = oor1 = false;
       }
-      mbar_wait_backoff(&sm.empty_bar[st], ((g / KB_STAGES) & 1) ^ 1);  // 192 spinning threads would starve the tail
-      uint8_t* t_h1 = stage + st * KB_STAGE + 2 * KB_G_PLANE;
+      // the remainder guide token's slice for the NEXT chunk (L2-resident) travels while this one is converted
+      float4 nq0 = gq0, nq1 = gq1;
+      if (n_rem == 1 && g + 1 < total) {
+        const int kn = (g + 1) % num_kc;
+        nq0 = __ldg(reinterpret_cast<const float4*>(grem + kn * KB_KC));
+        nq1 = __ldg(reinterpret_cast<const float4*>(grem + kn * KB_KC) + 1);
+      }
+      mbar_wait_backoff(&sm.rfull[rs], (g / KB_RSTAGES) & 1);
+      if (tt == 0) KB_CSTAMP(g, 1);
+      mbar_wait_backoff(&sm.pempty[st], ((g / KB_PSTAGES) & 1) ^ 1);  // backoff: 128 spinning threads would starve the tail
+      const uint32_t rsrc = smem_u32(raw + rs * KB_RSTAGE);
+      uint8_t* t_h1 = stage + st * KB_PSTAGE + 2 * KB_G_PLANE;
       uint8_t* t_h2 = t_h1 + KB_T_PLANE;
+      const float gq[8] = {gq0.x, gq0.y, gq0.z, gq0.w, gq1.x, gq1.y, gq1.z, gq1.w};
+      const uint32_t s_h1 = smem_u32(t_h1), s_h2 = smem_u32(t_h2);
+      float4 rr0[KB_ITEMS], rr1[KB_ITEMS];
+#pragma unroll
+      for (int j = 0; j < KB_ITEMS; ++j) {  // every load of the chunk first: five independent 32-byte reads in flight
+        const int f = tt + j * KB_FEED_THREADS;
+        rr0[j] = lds128(rsrc + f * 32);
+        rr1[j] = lds128(rsrc + f * 32 + 16);
+      }
 #pragma unroll
       for (int j = 0; j < KB_ITEMS; ++j) {
         const int f = tt + j * KB_FEED_THREADS;
-        if (f < KB_NTXT * 8) {
-          const float x[8] = {rb[j][0].x, rb[j][0].y, rb[j][0].z, rb[j][0].w,
-                              rb[j][1].x, rb[j][1].y, rb[j][1].z, rb[j][1].w};
-          uint32_t ph[4], pl[4];
-          bool bad = false;
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float x0 = x[2 * q] * TEXT_SCALE, x1 = x[2 * q + 1] * TEXT_SCALE;
-            bad |= !(fabsf(x0) < 65504.f) | !(fabsf(x1) < 65504.f);
-            const __half a0 = __float2half_rn(x0), a1 = __float2half_rn(x1);
-            const __half b0 = __float2half_rn(x0 - __half2float(a0)), b1 = __float2half_rn(x1 - __half2float(a1));
-            ph[q] = static_cast<uint32_t>(__half_as_ushort(a0)) | (static_cast<uint32_t>(__half_as_ushort(a1)) << 16);
-            pl[q] = static_cast<uint32_t>(__half_as_ushort(b0)) | (static_cast<uint32_t>(__half_as_ushort(b1)) << 16);
-          }
-          oor0 |= bad && (f >> 3) < NPAD;
-          oor1 |= bad && (f >> 3) >= NPAD;
-          const uint32_t off = sw128_offset(f >> 3, f & 7);
-          *reinterpret_cast<uint4*>(t_h1 + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-          *reinterpret_cast<uint4*>(t_h2 + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-          float ss = ssb[j], ra = racc[j];
-          const float gq[8] = {gq0.x, gq0.y, gq0.z, gq0.w, gq1.x, gq1.y, gq1.z, gq1.w};
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            ss += x[q] * x[q];
-            ra = fmaf(x[q], gq[q], ra);
-          }
-          ssb[j] = ss;
-          racc[j] = ra;
+        const int row = f >> 2;
+        float4 r0 = rr0[j], r1 = rr1[j];
+        if (row >= NPAD && n_here != KB_NP) {  // rows T..79 arrive zero-filled by TMA; a missing prompt is not loaded
+          r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          r1 = r0;
         }
+        const float x[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        uint32_t ph[4], pl[4];
+        float am = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // two-term split of a pair: one packed conversion per plane (cvt.rn.f16x2.f32), the residual is exact in fp32
+          const float x0 = x[2 * q] * TEXT_SCALE, x1 = x[2 * q + 1] * TEXT_SCALE;
+          am = fmaxf(am, fmaxf(fabsf(x0), fabsf(x1)));
+          const __half2 h = __floats2half2_rn(x0, x1);
+          const float2 hf = __half22float2(h);
+          const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+          ph[q] = *reinterpret_cast<const uint32_t*>(&h);
+          pl[q] = *reinterpret_cast<const uint32_t*>(&l);
+        }
+        // |x| 2^6 must stay below the fp16 maximum; NaN / inf inputs surface in the row's sum of squares (batch end)
+        const bool bad = !(am < 65504.f);
+        oor0 |= bad && row < NPAD;
+        oor1 |= bad && row >= NPAD;
+        const uint32_t off = sw64_offset(row, f & 3);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_h1 + off), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3])
+                     : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(s_h2 + off), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3])
+                     : "memory");
+        float ss = ssb[j], ra = racc[j];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          ss += x[q] * x[q];
+          ra = fmaf(x[q], gq[q], ra);
+        }
+        ssb[j] = ss;
+        racc[j] = ra;
       }
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.full_bar[st]);
-      if (g + 1 < total) load_chunk(g + 1);  // in flight while the MMAs of this chunk run
+      if (lane == 0) {
+        mbar_arrive(&sm.pfull[st]);
+        mbar_arrive(&sm.rempty[rs]);
+      }
+      if (tt == 0) KB_CSTAMP(g, 3);
+      gq0 = nq0;
+      gq1 = nq1;
       if (kc == num_kc - 1) {
         // end of a batch: column scales, remainder dot products, range flags -> the tail warps
         const int slot = bl & 1;
 #pragma unroll
         for (int j = 0; j < KB_ITEMS; ++j) {
-          float ss = ssb[j], rs = racc[j];
+          float ss = ssb[j], rs2 = racc[j];
           ss += __shfl_xor_sync(0xffffffffu, ss, 1);
           ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-          ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-          rs += __shfl_xor_sync(0xffffffffu, rs, 1);
-          rs += __shfl_xor_sync(0xffffffffu, rs, 2);
-          rs += __shfl_xor_sync(0xffffffffu, rs, 4);
+          rs2 += __shfl_xor_sync(0xffffffffu, rs2, 1);
+          rs2 += __shfl_xor_sync(0xffffffffu, rs2, 2);
           const int f = tt + j * KB_FEED_THREADS;
-          if ((f & 7) == 0 && f < KB_NTXT * 8) {
-            const int row = f >> 3, pp = row / NPAD, rr = row - pp * NPAD;
+          if ((f & 3) == 0) {
+            const int row = f >> 2, pp = row / NPAD, rr = row - pp * NPAD;
             sm.sbn[slot][pp][rr] = (1.0f / sqrtf(ss)) * (100.0f * 1.4426950408889634f / (TEXT_SCALE * GUIDE_SCALE));
-            sm.rem[slot][pp][rr] = rs * (1.0f / sqrtf(ss));
+            sm.rem[slot][pp][rr] = rs2 * (1.0f / sqrtf(ss));
+            if (!(ss <= 3.0e38f)) {  // a NaN or inf somewhere in the row (fmaxf above drops NaNs)
+              if (pp == 0) oor0 = true;
+              else oor1 = true;
+            }
           }
         }
         if (oor0) sm.range_flag[slot][0] = 1;
@@ -1285,10 +1448,35 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         if (tt == 0) KB_STAMP(bl, 8);
       }
     }
+    // nothing left to feed: help blending the LAST decision table (never recycled, so the extra exit tokens of
+    // these warps cannot satisfy another table's reuse check early)
+    const int units = my_batches * a.n_params;
+    if (units > 0) {
+      const int u = units - 1, bl = my_batches - 1, p = a.n_params - 1;
+      const int p0 = p_lo + bl * KB_NP;
+      mbar_wait_backoff(&sm.last_full, 0);  // (maps_full phases alias every other table: its own barrier)
+      kb_blend_steal(sm.m[u & 1], &sm.row_next[u & 3], &sm.rows_done[u & 3], min(KB_NP, p_hi - p0) * T, T, D,
+                     a.text + static_cast<size_t>(p0) * T * D, a.guide,
+                     a.out + (static_cast<size_t>(p0) * a.n_params + p) * T * D, static_cast<size_t>(a.n_params) * T * D, lane);
+    }
+  } else if (warp < KB_TAIL_WARP0) {
+    // ================================================================ dedicated blend warps: every decision table,
+    // in order, as soon as the tail warps publish it
+    const int units = my_batches * a.n_params;
+    for (int u = 0; u < units; ++u) {
+      const int bl = u / a.n_params, p = u - bl * a.n_params;
+      const int p0 = p_lo + bl * KB_NP;
+      const int n_here = min(KB_NP, p_hi - p0);
+      mbar_wait(&sm.maps_full[u & 1], (u >> 1) & 1);
+      kb_blend_steal(sm.m[u & 1], &sm.row_next[u & 3], &sm.rows_done[u & 3], n_here * T, T, D,
+                     a.text + static_cast<size_t>(p0) * T * D, a.guide,
+                     a.out + (static_cast<size_t>(p0) * a.n_params + p) * T * D, static_cast<size_t>(a.n_params) * T * D, lane);
+      if (warp == 2 + KB_FEED_WARPS && lane == 0 && p == 0) KB_STAMP(bl, 5);
+    }
   } else {
-    // ================================================================ tail: softmax, mapping, weights, blend
-    const int tw = warp - (2 + KB_FEED_WARPS);          // 0..7
-    const int ttid = tid - (2 + KB_FEED_WARPS) * 32;    // 0..255
+    // ================================================================ tail: softmax, mapping, weights
+    const int tw = warp - KB_TAIL_WARP0;                // 0..7
+    const int ttid = tid - KB_TAIL_WARP0 * 32;          // 0..255
     const int tile = tw >> 2, quarter = tw & 3;
     const int gi = tile * 128 + quarter * 32 + lane;    // guide token of this thread's TMEM lane
     const bool gi_valid = gi < a.a_mma;
@@ -1303,6 +1491,7 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
       }
     }
     named_bar_sync(1, KB_TAIL_THREADS);
+    int unit = 0;  // (batch, parameter set) pairs handed to the blend warps so far
     for (int bl = 0; bl < my_batches; ++bl) {
       const int p0 = p_lo + bl * KB_NP;  // first prompt of this batch
       const int slot = bl & 1;
@@ -1413,8 +1602,8 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
         for (int q = 0; q < 3; ++q) {
           const int r = lane + 32 * q;
           if (r < ncol) {
-            sm.part.v[pp][tw][r] = keep_e[q] ? keep_v[q] : 0u;
-            sm.part.i[pp][tw][r] = keep_e[q] ? gb_k + __ffs(keep_e[q]) - 1 : -1;
+            sm.part_v[pp][tw][r] = keep_e[q] ? keep_v[q] : 0u;
+            sm.part_i[pp][tw][r] = keep_e[q] ? gb_k + __ffs(keep_e[q]) - 1 : -1;
           }
         }
         if (gi < ncol && gi_valid) sm.diag[pp][gi] = dg;
@@ -1464,8 +1653,8 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
           int bi = -1;
 #pragma unroll
           for (int w = 0; w < KB_TAIL_WARPS; ++w) {
-            const int i = sm.part.i[pp][w][r];
-            const float sv = __uint_as_float(sm.part.v[pp][w][r]);
+            const int i = sm.part_i[pp][w][r];
+            const float sv = __uint_as_float(sm.part_v[pp][w][r]);
             if (i >= 0 && (bi < 0 || sv > bs)) {
               bs = sv;
               bi = i;
@@ -1484,30 +1673,45 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
       }
       named_bar_sync(1, KB_TAIL_THREADS);
       if (ttid == 0) KB_STAMP(bl, 3);
-      // ---- per parameter set: mapping by mode, weights (one warp per prompt), blend
-      for (int p = 0; p < a.n_params; ++p) {
+      // ---- per parameter set: mapping by mode, weights (one warp per prompt) -> decision table `unit & 1`
+      for (int p = 0; p < a.n_params; ++p, ++unit) {
         const fd_tween_params prm = p < KB_PRM ? sm.prm[p] : a.params[p];
+        const int ms = unit & 1;
+        KbMaps& mp = sm.m[ms];
+        if (unit >= 2) {
+          // table `ms` still belongs to unit - 2 until every one of its rows has been blended; its row counters
+          // (unit + 2) & 3 are recycled for unit + 2, which nobody can reach before this unit is published
+          if (ttid == 0) {
+            const int n_prev = min(KB_NP, p_hi - (p_lo + ((unit - 2) / a.n_params) * KB_NP)) * T;
+            // (every row + one exit token from each of the 8 tail and 2 dedicated warps)
+            while (*reinterpret_cast<volatile int*>(&sm.rows_done[(unit - 2) & 3]) < n_prev + KB_TAIL_WARPS + KB_BLEND_WARPS)
+              __nanosleep(64);
+            sm.row_next[(unit + 2) & 3] = 0;
+            sm.rows_done[(unit + 2) & 3] = 0;
+          }
+          named_bar_sync(1, KB_TAIL_THREADS);
+        }
         for (int idx = ttid; idx < n_here * KB_MT; idx += KB_TAIL_THREADS) {
           const int pp = idx / KB_MT, r = idx - pp * KB_MT;
-          float ms = 0.f;
+          float ms_v = 0.f;
           int mi = 0;
           if (prm.align_mode == FD_GUIDE_ORDER_DIRECT) {
             if (r < ncol && r < A) {  // guidance.py:60-69
               mi = r;
-              ms = (n_rem == 1 && r == a.a_mma) ? sm.prem[pp][r + 1] : sm.diag[pp][r];
+              ms_v = (n_rem == 1 && r == a.a_mma) ? sm.prem[pp][r + 1] : sm.diag[pp][r];
             }
           } else if (r < ncol) {
             // guidance.py:57-59,70-84 with reuse; a column whose maximum is exactly 0.0 keeps being
             // overwritten (Q4) and ends at the last guide token
             if (sm.amax_s[pp][r] > 0.f) {
-              ms = sm.amax_s[pp][r];
+              ms_v = sm.amax_s[pp][r];
               mi = sm.amax_i[pp][r];
             } else {
               mi = A - 1;
             }
           }
-          sm.m.map_s[pp][r] = ms;
-          sm.m.map_idx[pp][r] = mi;
+          mp.map_s[pp][r] = ms_v;
+          mp.map_idx[pp][r] = mi;
         }
         named_bar_sync(1, KB_TAIL_THREADS);
 #ifndef KB_X_SKIP_WEIGHTS
@@ -1517,25 +1721,28 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
 #endif
         {
           const int pp = tw;
-          const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
+          const K1MapView mv = {mp.map_s[pp], mp.map_idx[pp], mp.iw[pp], mp.sel[pp], mp.slerp_a[pp], mp.slerp_b[pp]};
           const size_t bp = static_cast<size_t>(p0 + pp) * a.n_params + p;
           k1_weights_warp(prm, mv, p < KB_PRM ? sm.lin_w[p] : a.lin_w + static_cast<size_t>(p) * T, T, lane, bp, a,
                           sm.range_flag[slot][pp]);
         }
         named_bar_sync(1, KB_TAIL_THREADS);
-        if (ttid == 0 && p == 0) KB_STAMP(bl, 4);
-        for (int pp = 0; pp < n_here; ++pp) {
-          const K1MapView mv = {sm.m.map_s[pp], sm.m.map_idx[pp], sm.m.iw[pp], sm.m.sel[pp], sm.m.slerp_a[pp], sm.m.slerp_b[pp]};
-          const float* text = a.text + static_cast<size_t>(p0 + pp) * T * D;
-          if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
-            k1_slerp_rows(mv, text, a.guide, T, D, tw, KB_TAIL_WARPS, lane);
-            named_bar_sync(1, KB_TAIL_THREADS);
+        if (prm.blend_mode == FD_BLEND_MODE_SLERP) {
+          for (int pp = 0; pp < n_here; ++pp) {
+            const K1MapView mv = {mp.map_s[pp], mp.map_idx[pp], mp.iw[pp], mp.sel[pp], mp.slerp_a[pp], mp.slerp_b[pp]};
+            k1_slerp_rows(mv, a.text + static_cast<size_t>(p0 + pp) * T * D, a.guide, T, D, tw, KB_TAIL_WARPS, lane);
           }
-          const size_t bp = static_cast<size_t>(p0 + pp) * a.n_params + p;
-          k1_blend_rows_warp(mv, text, a.guide, a.out + bp * T * D, T, D, tw, KB_TAIL_WARPS, lane);
+          named_bar_sync(1, KB_TAIL_THREADS);
         }
-        named_bar_sync(1, KB_TAIL_THREADS);
-        if (ttid == 0 && p == 0) KB_STAMP(bl, 5);
+        if (ttid == 0) {
+          mbar_arrive(&sm.maps_full[ms]);  // release: the named barrier above ordered every tail thread's writes
+          if (bl == my_batches - 1 && p == a.n_params - 1) mbar_arrive(&sm.last_full);
+          if (p == 0) KB_STAMP(bl, 4);
+        }
+        // the tail warps have nothing to do until the next accumulator is complete: help with the rows
+        kb_blend_steal(mp, &sm.row_next[unit & 3], &sm.rows_done[unit & 3], n_here * T, T, D,
+                       a.text + static_cast<size_t>(p0) * T * D, a.guide,
+                       a.out + (static_cast<size_t>(p0) * a.n_params + p) * T * D, static_cast<size_t>(a.n_params) * T * D, lane);
       }
     }
   }
@@ -1645,24 +1852,32 @@ extern "C" int fd_sim_blend(const float* text_dev, const float* guide_dev, int n
   {
     // the mapping modes decide the kernel, so the fast path needs the host copy of the parameters
     bool eligible = g_k1_fast && params_host != nullptr && guide_batch == 1 && a_mma > 128 && a_mma <= 256 &&
-                    A - a_mma <= 1 && n_text >= g_k1_fast_min_prompts;
+                    A - a_mma <= 1 && n_text >= g_k1_fast_min_prompts && D <= KB_MAX_D;
     for (int q = 0; eligible && q < n_params; ++q)
       eligible = params_host[q].align_mode == FD_GUIDE_ORDER_DIRECT || params_host[q].mapping_reuse != 0;
     if (eligible) {
-      CUtensorMap t1, t2;
+      CUtensorMap t1, t2, tt;
       for (int which = 0; which < 2; ++which) {
         uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(a_mma), 1};
         uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, static_cast<uint64_t>(A) * D * 2};
-        uint32_t box[3] = {KC, 256, 1};
+        uint32_t box[3] = {KB_KC, 256, 1};
         rc = encode_tmap(which ? &t2 : &t1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
-                         which ? static_cast<const void*>(g_lo) : g_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+                         which ? static_cast<const void*>(g_lo) : g_hi, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+        if (rc != FD_OK) return rc;
+      }
+      {
+        // raw fp32 text: {D, T, prompts}, box 32 floats x 80 rows (rows T..79 are out of bounds: zero-filled)
+        uint64_t dims[3] = {static_cast<uint64_t>(D), static_cast<uint64_t>(T), static_cast<uint64_t>(n_text)};
+        uint64_t strides[2] = {static_cast<uint64_t>(D) * 4, static_cast<uint64_t>(T) * D * 4};
+        uint32_t box[3] = {KB_KC, NPAD, 1};
+        rc = encode_tmap(&tt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, text_dev, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
         if (rc != FD_OK) return rc;
       }
       const int sms_b = sm_count();
       if (sms_b <= 0) return set_error(FD_ERR_CUDA, "fd_sim_blend: cannot query SM count");
       const int n_batches = (n_text + KB_NP - 1) / KB_NP;  // fewer CTAs than SMs only when a CTA would hold < 2 prompts
       FD_CUDA_OK(cudaFuncSetAttribute(k1b_sim_blend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KB_SMEM_BYTES));
-      k1b_sim_blend_kernel<<<n_batches < sms_b ? n_batches : sms_b, KB_THREADS, KB_SMEM_BYTES, cst>>>(t1, t2, a);
+      k1b_sim_blend_kernel<<<n_batches < sms_b ? n_batches : sms_b, KB_THREADS, KB_SMEM_BYTES, cst>>>(t1, t2, tt, a);
       FD_CUDA_OK(cudaGetLastError());
       return FD_OK;
     }

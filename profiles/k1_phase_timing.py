@@ -8,7 +8,7 @@ dev = torch.device('cuda:0')
 lib = _native.lib()
 lib.fd_debug_set_k1_timing.argtypes = [ctypes.c_void_p]
 buf = torch.zeros(256, dtype=torch.int64, device=dev)
-for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
+for nb, mode, reuse in [(1024, 1, 1)]:
     txt = torch.randn(nb, 77, 768, device=dev)
     img = torch.randn(1, 257, 768, device=dev)
     prm = _native.TweenParams()
@@ -28,10 +28,16 @@ for nb, mode, reuse in [(1, 1, 1), (1024, 1, 1), (1024, 1, 0), (1024, 0, 0)]:
           f'phases ns {[t[i] - t[0] for i in range(6)]} softmax-internal {[t[6]-t[0], t[7]-t[0]]}')
     if t[64 + 9]:  # batched kernel: per-batch events of CTA 0, ns from the first MMA commit's batch start
         t0 = min(x for x in t[64:64 + 16 * 8] if x)
-        for bl in range(8):
+        for bl in range(4):
             ev = t[64 + 16 * bl: 64 + 16 * bl + 10]
             if ev[9]:
                 print('   batch', bl, {k: (ev[i] - t0 if ev[i] else None) for k, i in
                                        (('feed_done', 8), ('mma_done', 9), ('norms', 0), ('acc', 1), ('drained', 2),
                                         ('combined', 3), ('weights', 4), ('blend', 5))})
+        if t[128]:
+            c0 = t[128]
+            print('   chunks of batch 1 (ns from the first guide request): guide_req, raw_seen, raw_req, feed_done, mma_full, mma_issued')
+            for c in range(16):
+                print('    ', c, [t[128 + 6 * c + e] - c0 if t[128 + 6 * c + e] else None for e in range(6)])
+        print('   isolated MMA chunk: issue end -> commit visible (ns):', [t[225 + 2 * k] - t[224 + 2 * k] for k in range(4)])
     buf.zero_()
