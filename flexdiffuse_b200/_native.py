@@ -31,7 +31,8 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_groupnorm_act_workspace_bytes', 'fd_groupnorm_act',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
                'fd_composite_eps', 'fd_image_tail_u8', 'fd_visual_projection',
-               'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag')
+               'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
+               'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3', 'fd_linear_x3_flag')
 
 
 class NativeError(RuntimeError):
@@ -139,6 +140,13 @@ def lib() -> C.CDLL:
     l.fd_visual_projection.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_int64, C.c_int, vp]
     l.fd_visual_projection.restype = C.c_int
     l.fd_visual_projection_range_flag.restype = C.c_int
+    l.fd_linear_x3_operand_bytes.argtypes = [C.c_int, C.c_int]
+    l.fd_linear_x3_operand_bytes.restype = C.c_int64
+    l.fd_linear_x3_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
+    l.fd_linear_x3_split.restype = C.c_int
+    l.fd_linear_x3.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp]
+    l.fd_linear_x3.restype = C.c_int
+    l.fd_linear_x3_flag.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -550,3 +558,65 @@ def visual_projection(hidden: torch.Tensor, weight: torch.Tensor) -> torch.Tenso
     check(rc, 'fd_visual_projection')
     count_launch(2 if changed else 1)
     return out.reshape(*hidden.shape[:-1], N)
+
+
+# --------------------------------------------------------------------------- K11
+LINEAR_ACT_NONE, LINEAR_ACT_QUICK_GELU, LINEAR_ACT_GELU = 0, 1, 2
+_x3_weights = {}     # (data_ptr, version, N, K) -> (operand buffer, the weight tensor it was made from)
+
+
+def x3_split(x2d: torch.Tensor) -> torch.Tensor:
+    '''fd_linear_x3_split: fp32 [rows, K] -> operand buffer (two fp16 planes + inverse row scales).'''
+    _need(x2d, 'x', torch.float32)
+    rows, K = x2d.shape
+    buf = torch.empty(lib().fd_linear_x3_operand_bytes(rows, K), dtype=torch.uint8, device=x2d.device)
+    check(lib().fd_linear_x3_split(ptr(x2d), rows, K, ptr(buf), buf.numel(), stream_ptr(x2d.device)),
+          'fd_linear_x3_split')
+    count_launch()
+    return buf
+
+
+def x3_weight_operand(weight: torch.Tensor) -> torch.Tensor:
+    '''Split planes of a weight matrix, cached per (storage, version); the cache keeps the weight alive so
+    its address cannot be recycled under a stale entry.'''
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape))
+    ent = _x3_weights.get(key)
+    if ent is None:
+        if len(_x3_weights) > 1024:
+            _x3_weights.clear()
+        ent = (x3_split(weight.detach()), weight)
+        _x3_weights[key] = ent
+    return ent[0]
+
+
+def linear_x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              act: int = LINEAR_ACT_NONE, operand: Optional[torch.Tensor] = None,
+              split_k: Optional[int] = None) -> torch.Tensor:
+    '''fd_linear_x3: act(x[..., K] @ weight[N, K]^T + bias) in fp32 accuracy on tcgen05.  `operand` is the
+    result of `x3_split` on the same (flattened) x, for callers that feed one input to several Linears.'''
+    _need(weight, 'weight', torch.float32)
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise NativeError('linear_x3 needs CUDA float32 input')
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, K = x2.shape
+    N = weight.shape[0]
+    if weight.shape[1] != K:
+        raise NativeError(f'linear_x3: weight is {tuple(weight.shape)}, input has K={K}')
+    if bias is not None:
+        _need(bias, 'bias', torch.float32)
+    if operand is None:
+        operand = x3_split(x2)
+    wop = x3_weight_operand(weight)
+    if split_k is None:
+        tiles = ((M + 127) // 128) * ((N + 127) // 128)
+        split_k = 1
+        while split_k < 8 and tiles * split_k < 64 and K // 64 // (split_k * 2) >= 4:
+            split_k *= 2
+    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
+    partial = (torch.empty((split_k, M, N), dtype=torch.float32, device=x.device) if split_k > 1 else None)
+    check(lib().fd_linear_x3(ptr(operand), M, ptr(wop), N, K, ptr(bias), act, ptr(out), ptr(partial),
+                             split_k, stream_ptr(x.device)), 'fd_linear_x3')
+    count_launch(2 if split_k > 1 else 1)
+    return out.reshape(*x.shape[:-1], N)

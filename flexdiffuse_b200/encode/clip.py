@@ -1,10 +1,11 @@
 '''CLIP encoders -- API mirror of /root/reference/encode/clip.py.
 
 `preprocess` (clip.py:15-39) and `CLIPEncoder.prompt / .image` (clip.py:47-100) keep the
-reference's signatures and numerics.  The transformer towers stay in PyTorch
-(transformers' CLIPModel); BASELINE.json's north_star only moves the similarity /
-blend stage that consumes these embeddings onto hand-written kernels (K1).  On a CUDA
-device each tower forward is captured once per input shape and replayed as a CUDA graph.
+reference's signatures and numerics.  The weights, embeddings, layer norms and the attention
+core stay transformers' / PyTorch's; on an sm_100 device every Linear of the two encoders
+(q / k / v / out_proj, fc1 + activation, fc2 -- 99 % of the towers' arithmetic) runs on K11
+`fd_linear_x3`, an fp32-accurate tcgen05 GEMM, and `visual_projection` on
+K1P.  Each tower forward is captured once per input shape and replayed as a CUDA graph.
 '''
 from __future__ import annotations
 
@@ -73,17 +74,59 @@ class _matmul_precision:
         torch.backends.cuda.matmul.allow_tf32 = self.old
 
 
+_X3_ACTS = {'quick_gelu': 1, 'gelu': 2}
+
+
+def _x3_ok(encoder, hidden: torch.Tensor) -> bool:
+    '''K11 serves fp32 CUDA towers whose widths are multiples of 64 (every CLIP variant).'''
+    if not (hidden.is_cuda and hidden.dtype == torch.float32) or not len(encoder.layers):
+        return False
+    l0 = encoder.layers[0]
+    return (l0.mlp.fc1.in_features % 64 == 0 and l0.mlp.fc1.out_features % 64 == 0
+            and l0.mlp.fc1.weight.dtype == torch.float32)
+
+
+def _x3_encoder(encoder, hidden: torch.Tensor, causal: bool) -> torch.Tensor:
+    '''transformers' CLIPEncoder.forward (pre-LN blocks: `x + attn(ln1(x))`, `x + mlp(ln2(x))`) with every
+    Linear on K11.  One split of the block input feeds q, k and v; fc1's bias and activation ride in
+    the GEMM epilogue; the attention core is torch SDPA in fp32 (causal for the text tower, as
+    CLIPTextTransformer builds its mask).'''
+    from torch.nn.functional import scaled_dot_product_attention as sdpa
+    from .. import _native
+    B, T, C = hidden.shape
+    for layer in encoder.layers:
+        at, mlp = layer.self_attn, layer.mlp
+        H = at.num_heads
+        x = layer.layer_norm1(hidden).reshape(B * T, C)
+        op = _native.x3_split(x)
+        q = _native.linear_x3(x, at.q_proj.weight, at.q_proj.bias, operand=op)
+        k = _native.linear_x3(x, at.k_proj.weight, at.k_proj.bias, operand=op)
+        v = _native.linear_x3(x, at.v_proj.weight, at.v_proj.bias, operand=op)
+        q, k, v = (t.view(B, T, H, C // H).transpose(1, 2) for t in (q, k, v))
+        o = sdpa(q, k, v, is_causal=causal, scale=at.scale).transpose(1, 2).reshape(B * T, C)
+        hidden = hidden + _native.linear_x3(o, at.out_proj.weight, at.out_proj.bias).view(B, T, C)
+        x = layer.layer_norm2(hidden).reshape(B * T, C)
+        act = _X3_ACTS.get(getattr(mlp.config, 'hidden_act', None), 0)
+        h = _native.linear_x3(x, mlp.fc1.weight, mlp.fc1.bias, act=act)
+        if not act:
+            h = mlp.activation_fn(h)
+        hidden = hidden + _native.linear_x3(h, mlp.fc2.weight, mlp.fc2.bias).view(B, T, C)
+    return hidden
+
+
 class CLIPEncoder():
-    def __init__(self, clip, token, cuda_graph: bool = True, tf32: bool = False) -> None:
-        '''`cuda_graph` / `tf32` are not reference arguments.  cuda_graph: on a CUDA device, replay
+    def __init__(self, clip, token, cuda_graph: bool = True, tf32: bool = False, x3: bool = True) -> None:
+        '''`cuda_graph` / `tf32` / `x3` are not reference arguments.  cuda_graph: on a CUDA device, replay
         each tower as a captured graph per input shape (call `invalidate()` after changing the CLIP
-        weights).  tf32: run the towers' fp32 GEMMs on the tensor cores in TF32 (~5x faster towers at
-        ~1e-3 relative error of the embeddings; OFF by default because the reference towers are
-        exact fp32 and K1's decisions sit on near-ties of 100 * cos).'''
+        weights).  x3 (default): the towers' Linears on K11, fp32-accurate on the tensor cores.
+        tf32 (only without x3): cuBLAS TF32 GEMMs, ~3e-4 relative error of the embeddings -- kept as the
+        comparison point, OFF by default because the reference towers are exact fp32 and K1's decisions
+        sit on near-ties of 100 * cos.'''
         self.clip = clip
         self.token = token
         self.cuda_graph = cuda_graph
         self.tf32 = tf32
+        self.x3 = x3
         self._graphs = {}
 
     def invalidate(self) -> None:
@@ -96,7 +139,7 @@ class CLIPEncoder():
             if not self.cuda_graph or torch.is_grad_enabled() \
                     or torch.cuda.is_current_stream_capturing():
                 return fn(x)
-            key = (kind, tuple(x.shape), x.dtype, self.tf32)
+            key = (kind, tuple(x.shape), x.dtype, self.tf32, self.x3)
             g = self._graphs.get(key)
             if g is None:
                 try:
@@ -113,8 +156,15 @@ class CLIPEncoder():
         ids = self.token(prompt, padding='max_length',
                          max_length=self.token.model_max_length,
                          truncation=True, return_tensors='pt').input_ids
-        return self._run('text', lambda i: self.clip.text_model(i)[0],
-                         ids.to(self.clip.device))
+        return self._run('text', self._text, ids.to(self.clip.device))
+
+    def _text(self, ids: torch.Tensor) -> torch.Tensor:
+        tm = self.clip.text_model
+        if self.x3 and ids.is_cuda:
+            hidden = tm.embeddings(input_ids=ids.view(-1, ids.shape[-1]))
+            if _x3_ok(tm.encoder, hidden):
+                return tm.final_layer_norm(_x3_encoder(tm.encoder, hidden, causal=True))
+        return tm(ids)[0]
 
     def image(self, image) -> torch.Tensor:
         '''All 257 vision tokens through post_layernorm and visual_projection
@@ -134,8 +184,11 @@ class CLIPEncoder():
     def _vision(self, x: torch.Tensor) -> torch.Tensor:
         vm = self.clip.vision_model
         hidden = vm.pre_layrnorm(vm.embeddings(x))
-        hidden = vm.encoder(inputs_embeds=hidden, output_attentions=False,
-                            output_hidden_states=False, return_dict=True)[0]
+        if self.x3 and _x3_ok(vm.encoder, hidden):
+            hidden = _x3_encoder(vm.encoder, hidden, causal=False)
+        else:
+            hidden = vm.encoder(inputs_embeds=hidden, output_attentions=False,
+                                output_hidden_states=False, return_dict=True)[0]
         hidden = vm.post_layernorm(hidden)
         proj = self.clip.visual_projection
         if (hidden.is_cuda and hidden.dtype == torch.float32 and proj.bias is None

@@ -193,11 +193,12 @@ class ConceptMapper():
 class Guide():
     def __init__(self, clip, tokenizer, device: str = 'cuda', tf32_towers: bool = False) -> None:
         '''Context for generating prompt / image embeddings and tweening them
-        (guidance.py:316-335).  `tf32_towers` (not a reference argument): see CLIPEncoder.'''
+        (guidance.py:316-335).  `tf32_towers` (not a reference argument): cuBLAS TF32 towers instead of the
+        default fp32-accurate K11 ones; see CLIPEncoder.'''
         self.clip = clip
         self.tokenizer = tokenizer
         self.device = device
-        self.encoder = CLIPEncoder(clip, tokenizer, tf32=tf32_towers)
+        self.encoder = CLIPEncoder(clip, tokenizer, tf32=tf32_towers, x3=not tf32_towers)
         # header token of this embed is used for direct image guidance
         self.placeholder_embed = self.encoder.prompt('{}')
 

@@ -204,6 +204,39 @@ int fd_visual_projection(const float* hidden_dev,   /* [M, K] fp32, M = images *
  * or non-finite), clearing the flag; synchronises the device.                                 */
 int fd_visual_projection_range_flag(void);
 
+/* ---- K11: fp32-accurate Linear on tcgen05 for the CLIP towers --------------------------- *
+ * Replaces the fp32 nn.Linear layers (q / k / v / out_proj, fc1, fc2) of the ViT-L/14 vision
+ * tower and of the text tower that encode/clip.py:57-65 (`clip.text_model(ids)`) and :86-100
+ * (`clip.vision_model...`) run through transformers' CLIPModel:
+ *     out[M, N] = act( x[M, K] . W[N, K]^T + bias[N] )        fp32 in, fp32 out
+ * Every operand row is scaled by a power of two chosen from its maximum and split into two fp16
+ * terms; three exact fp16 products accumulate in fp32 in TMEM, so the result has fp32 accuracy
+ * (no tf32 / bf16 rounding of the operands) at tensor-core speed.
+ *   1. fd_linear_x3_split     fp32 [rows, K] -> operand buffer (weights once per version,
+ *                             activations once per call; one buffer may feed several Linears)
+ *   2. fd_linear_x3           the GEMM + bias + activation on two operand buffers             */
+#define FD_LINEAR_ACT_NONE       0
+#define FD_LINEAR_ACT_QUICK_GELU 1   /* x * sigmoid(1.702 x): CLIP's hidden_act               */
+#define FD_LINEAR_ACT_GELU       2   /* erf GELU                                              */
+int64_t fd_linear_x3_operand_bytes(int rows, int K);
+int fd_linear_x3_split(const float* x_dev,      /* [rows, K] fp32 row-major, K % 64 == 0        */
+                       int rows, int K,
+                       void* operand_dev,       /* >= fd_linear_x3_operand_bytes, 256-B aligned  */
+                       int64_t operand_bytes, void* stream);
+int fd_linear_x3(const void* act_operand_dev,   /* split [M, K]                                  */
+                 int M,
+                 const void* weight_operand_dev,/* split [N, K]                                  */
+                 int N, int K,                  /* N % 4 == 0                                    */
+                 const float* bias_dev,         /* [N] fp32 or NULL                              */
+                 int act,                       /* FD_LINEAR_ACT_*                               */
+                 float* out_dev,                /* [M, N] fp32                                   */
+                 float* partial_dev,            /* [split_k, M, N] fp32 scratch, NULL if split_k == 1 */
+                 int split_k,                   /* 1..16: K is cut into this many slices, reduced in a fixed order */
+                 void* stream);
+/* 1 if a non-finite operand was split since the last call, >= 16 if a pipeline wait gave up;
+ * clears the flag; synchronises the device.                                                 */
+int fd_linear_x3_flag(void);
+
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
  * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'
  * CrossAttention.forward recomputes for each of the 16 attn2 layers at every step,

@@ -148,8 +148,8 @@ def test_tf32_towers_are_opt_in_and_close(native, cuda_dev):
     from flexdiffuse_b200.encode.clip import CLIPEncoder
     from tests.encode_helpers import FakeTok, test_images, tiny_clip
     clip = tiny_clip().to(cuda_dev)
-    exact = CLIPEncoder(clip, FakeTok(), cuda_graph=False)
-    fast = CLIPEncoder(clip, FakeTok(), tf32=True)
+    exact = CLIPEncoder(clip, FakeTok(), cuda_graph=False, x3=False)
+    fast = CLIPEncoder(clip, FakeTok(), tf32=True, x3=False)
     flag = torch.backends.cuda.matmul.allow_tf32
     with torch.no_grad():
         a, b = exact.image(test_images()[0]), fast.image(test_images()[0])
@@ -157,3 +157,49 @@ def test_tf32_towers_are_opt_in_and_close(native, cuda_dev):
     assert torch.backends.cuda.matmul.allow_tf32 == flag
     assert ((a - b).norm() / a.norm()).item() < 5e-3
     assert ((c - d).norm() / c.norm()).item() < 5e-3
+
+
+def _towers_vs_transformers(native, cuda_dev, clip, tol):
+    from flexdiffuse_b200.encode.clip import CLIPEncoder
+    from tests.encode_helpers import FakeTok, test_images
+    ours = CLIPEncoder(clip, FakeTok(), cuda_graph=True)                 # K11 towers (default), graphed
+    stock = CLIPEncoder(clip, FakeTok(), cuda_graph=False, x3=False)     # transformers' own fp32 forward
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            before = native.LAUNCHES
+            for img in test_images()[:2]:
+                a, b = ours.image(img), stock.image(img)
+                assert (a - b).abs().max().item() <= tol * b.abs().max().item(), ((a - b).abs().max().item(), b.abs().max().item())
+            for prompt in ('a red fox', 'an astronaut riding a horse on the moon, oil painting'):
+                c, d = ours.prompt(prompt), stock.prompt(prompt)
+                assert (c - d).abs().max().item() <= tol * d.abs().max().item()
+            assert native.LAUNCHES > before
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert native.lib().fd_linear_x3_flag() == 0
+    assert any(g for g in ours._graphs.values()), 'no tower was captured'
+
+
+def test_x3_towers_match_transformers_fp32_tiny(native, cuda_dev):
+    '''CLIPEncoder's default towers (every Linear on K11, attention on SDPA) against transformers' own fp32
+    forward of the same weights (encode/clip.py:57-65, 86-100): fp32-level agreement, 2e-5 of the output
+    scale (both sides are fp32-accurate; they differ by summation order).'''
+    from tests.encode_helpers import tiny_clip
+    _towers_vs_transformers(native, cuda_dev, tiny_clip().to(cuda_dev), 2e-5)
+
+
+def test_x3_towers_match_transformers_fp32_vit_l14_widths(native, cuda_dev):
+    '''Same at CLIP ViT-L/14 widths (vision 1024 / 4096 / 16 heads, text 768 / 3072 / 12 heads) with 3 layers
+    each: the shapes K11 runs in production (q / k / v / o 1024x1024, fc1 4096x1024, fc2 1024x4096 split-K).'''
+    from transformers import CLIPConfig, CLIPModel
+    cfg = CLIPConfig(
+        text_config=dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=3, num_attention_heads=12,
+                         vocab_size=49408, max_position_embeddings=77),
+        vision_config=dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=3, num_attention_heads=16,
+                           image_size=224, patch_size=14),
+        projection_dim=768)
+    torch.manual_seed(11)
+    clip = CLIPModel(cfg).eval().requires_grad_(False).to(cuda_dev)
+    _towers_vs_transformers(native, cuda_dev, clip, 2e-5)
