@@ -472,9 +472,10 @@ def _guide_rates(dev):
     rtf, gtf = guide_embeds_e2e(dev, tf32=True, clip=clip)
     return {'gpu_guide_embeds_calls_per_s': r32,
             'gpu_guide_embeds_calls_per_s_tf32_towers': rtf,
-            'tf32_towers_image_embedding_rel_l2_vs_fp32': ((gtf - g32).norm() / g32.norm()).item(),
-            'guide_embeds_note': 'fp32 towers (the reference\'s precision) are CUDA-core GEMM bound: 155 GFLOP of '
-                                 'fp32 per image; tf32_towers=True is the opt-in tensor-core variant'}
+            'tf32_towers_image_embedding_rel_l2_vs_default': ((gtf - g32).norm() / g32.norm()).item(),
+            'guide_embeds_note': 'default towers: every Linear on K11 (fp32-accurate three-product fp16 split on '
+                                 'tcgen05, 2e-5 of transformers\' fp32 output); tf32_towers=True is the cuBLAS TF32 '
+                                 'comparison point'}
 
 
 # ------------------------------------------------------------------ plain-torch GPU baseline
