@@ -32,7 +32,9 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_add_bias_residual', 'fd_add_layernorm', 'fd_geglu',
                'fd_composite_eps', 'fd_image_tail_u8', 'fd_visual_projection',
                'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
-               'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3', 'fd_linear_x3_flag')
+               'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3_split_ln', 'fd_linear_x3',
+               'fd_linear_x3_flag',
+               'fd_attention_f32')
 
 
 class NativeError(RuntimeError):
@@ -144,9 +146,14 @@ def lib() -> C.CDLL:
     l.fd_linear_x3_operand_bytes.restype = C.c_int64
     l.fd_linear_x3_split.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int64, vp]
     l.fd_linear_x3_split.restype = C.c_int
+    l.fd_linear_x3_split_ln.argtypes = [vp, C.c_int, C.c_int, vp, vp, C.c_float, vp, C.c_int64, vp]
+    l.fd_linear_x3_split_ln.restype = C.c_int
     l.fd_linear_x3.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, vp]
     l.fd_linear_x3.restype = C.c_int
     l.fd_linear_x3_flag.restype = C.c_int
+    l.fd_attention_f32.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_int, vp]
+    l.fd_attention_f32.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -576,6 +583,19 @@ def x3_split(x2d: torch.Tensor) -> torch.Tensor:
     return buf
 
 
+def x3_split_ln(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
+    '''fd_linear_x3_split_ln: operand buffer of LayerNorm(x2d) * gamma + beta (K % 128 == 0, K <= 2048).'''
+    _need(x2d, 'x', torch.float32)
+    _need(gamma, 'gamma', torch.float32)
+    _need(beta, 'beta', torch.float32)
+    rows, K = x2d.shape
+    buf = torch.empty(lib().fd_linear_x3_operand_bytes(rows, K), dtype=torch.uint8, device=x2d.device)
+    check(lib().fd_linear_x3_split_ln(ptr(x2d), rows, K, ptr(gamma), ptr(beta), float(eps), ptr(buf), buf.numel(),
+                                      stream_ptr(x2d.device)), 'fd_linear_x3_split_ln')
+    count_launch()
+    return buf
+
+
 def x3_weight_operand(weight: torch.Tensor) -> torch.Tensor:
     '''Split planes of a weight matrix, cached per (storage, version); the cache keeps the weight alive so
     its address cannot be recycled under a stale entry.'''
@@ -589,34 +609,74 @@ def x3_weight_operand(weight: torch.Tensor) -> torch.Tensor:
     return ent[0]
 
 
-def linear_x3(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+def linear_x3(x: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
               act: int = LINEAR_ACT_NONE, operand: Optional[torch.Tensor] = None,
-              split_k: Optional[int] = None) -> torch.Tensor:
-    '''fd_linear_x3: act(x[..., K] @ weight[N, K]^T + bias) in fp32 accuracy on tcgen05.  `operand` is the
-    result of `x3_split` on the same (flattened) x, for callers that feed one input to several Linears.'''
+              split_k: Optional[int] = None, residual: Optional[torch.Tensor] = None,
+              rows: Optional[int] = None) -> torch.Tensor:
+    '''fd_linear_x3: residual + act(x[..., K] @ weight[N, K]^T + bias) in fp32 accuracy on tcgen05.  `operand` is
+    the result of `x3_split` / `x3_split_ln` on the same (flattened) input, for callers that feed one input to
+    several Linears or never materialise it (then pass x=None and `rows`).  Returns [..., N] ([rows, N] without x).'''
     _need(weight, 'weight', torch.float32)
-    if x.dtype != torch.float32 or not x.is_cuda:
-        raise NativeError('linear_x3 needs CUDA float32 input')
-    x2 = x.reshape(-1, x.shape[-1])
-    if not x2.is_contiguous():
-        x2 = x2.contiguous()
-    M, K = x2.shape
-    N = weight.shape[0]
-    if weight.shape[1] != K:
-        raise NativeError(f'linear_x3: weight is {tuple(weight.shape)}, input has K={K}')
+    N, K = weight.shape
+    if x is not None:
+        if x.dtype != torch.float32 or not x.is_cuda:
+            raise NativeError('linear_x3 needs CUDA float32 input')
+        x2 = x.reshape(-1, x.shape[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        if x2.shape[1] != K:
+            raise NativeError(f'linear_x3: weight is {tuple(weight.shape)}, input has K={x2.shape[1]}')
+        if operand is None:
+            operand = x3_split(x2)
+    else:
+        if operand is None or rows is None:
+            raise NativeError('linear_x3: without x, pass the split operand and its row count')
+        M = rows
+    dev = weight.device
     if bias is not None:
         _need(bias, 'bias', torch.float32)
-    if operand is None:
-        operand = x3_split(x2)
     wop = x3_weight_operand(weight)
     if split_k is None:
-        tiles = ((M + 127) // 128) * ((N + 127) // 128)
-        split_k = 1
-        while split_k < 8 and tiles * split_k < 64 and K // 64 // (split_k * 2) >= 4:
-            split_k *= 2
-    out = torch.empty((M, N), dtype=torch.float32, device=x.device)
-    partial = (torch.empty((split_k, M, N), dtype=torch.float32, device=x.device) if split_k > 1 else None)
-    check(lib().fd_linear_x3(ptr(operand), M, ptr(wop), N, K, ptr(bias), act, ptr(out), ptr(partial),
-                             split_k, stream_ptr(x.device)), 'fd_linear_x3')
-    count_launch(2 if split_k > 1 else 1)
-    return out.reshape(*x.shape[:-1], N)
+        # measured on the tower shapes (profiles/k11_bench.py): a second K slice pays while the grid is under
+        # ~100 CTAs; long K wants 4 (M > 128) or 8 slices
+        if K >= 3072:
+            split_k = 4 if M > 128 else 8
+        elif K >= 768 and N <= 3072:
+            split_k = 2
+        else:
+            split_k = 1
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    if residual is not None:
+        _need(residual, 'residual', torch.float32)
+        if residual.numel() != M * N:
+            raise NativeError(f'linear_x3: residual has {residual.numel()} elements, need {M * N}')
+    check(lib().fd_linear_x3(ptr(operand), M, ptr(wop), N, K, ptr(bias), act, ptr(residual), ptr(out), split_k,
+                             stream_ptr(dev)), 'fd_linear_x3')
+    count_launch()
+    return out.reshape(*x.shape[:-1], N) if x is not None else out
+
+
+# --------------------------------------------------------------------------- K12
+def attention_f32_supported(T: int, d: int) -> bool:
+    '''Shapes K12 serves: K^T, V, the query rows and the probability strips of one head fit in shared memory.'''
+    ni = 3 if T <= 96 else 9
+    floats = d * (T | 1) + T * d + 8 * d * 4 + 8 * 32 * ni * 4
+    return T <= 288 and d % 4 == 0 and d <= 128 and floats * 4 <= 227 * 1024
+
+
+def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: float,
+                  causal: bool = False) -> torch.Tensor:
+    '''fd_attention_f32.  q / k / v: [B, T, C] fp32 views with unit stride along C and one common token
+    stride (e.g. the three column blocks of a fused q|k|v projection); returns [B, T, C] contiguous.'''
+    B, T, Cc = q.shape
+    for t, name in ((q, 'q'), (k, 'k'), (v, 'v')):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise NativeError(f'attention_f32: {name} must be CUDA float32')
+        if t.shape != q.shape or t.stride(2) != 1 or t.stride(1) != q.stride(1) or t.stride(0) != T * q.stride(1):
+            raise NativeError(f'attention_f32: {name} must share q\'s [B, T, C] layout (unit channel stride)')
+    out = torch.empty((B, T, Cc), dtype=torch.float32, device=q.device)
+    check(lib().fd_attention_f32(ptr(q), ptr(k), ptr(v), q.stride(1), ptr(out), B, T, heads, Cc // heads,
+                                 float(scale), int(causal), stream_ptr(q.device)), 'fd_attention_f32')
+    count_launch()
+    return out

@@ -15,9 +15,9 @@
 //                           version, activations once per call; one warp per row)
 //   k11_gemm_kernel<BN>     both operands by TMA (SWIZZLE_128B, K chunks of 64, multi-stage ring),
 //                           warp 0 producer, warp 1 MMA issuer (M128 N=BN K16, three products per k-step),
-//                           warps 2-5 epilogue: TMEM -> x inv_a[row] x inv_w[col] (+ bias, activation) ->
-//                           fp32 global, or split-K partials
-//   k11_reduce_kernel       split-K partials in a fixed order (+ bias, activation)
+//                           warps 2-5 epilogue: TMEM -> x inv_a[row] x inv_w[col] (+ bias, activation, residual) ->
+//                           fp32 global; with split-K the last CTA of a tile to finish adds the slices in ascending order
+//   k11_ln_split_kernel     LayerNorm fused with the split (the towers' pre-LN blocks feed every q|k|v and fc1 GEMM)
 #include <cuda_fp16.h>
 
 #include "fd_common.cuh"
@@ -74,11 +74,76 @@ __global__ void __launch_bounds__(256) k11_split_rows_kernel(const float* __rest
   }
 }
 
+// LayerNorm fused with the operand split: y = (x - mean) rstd gamma + beta never leaves the registers of the warp that owns
+// the row; only the two fp16 planes and the inverse scale are written.  K = 128 V floats per row (V float4 per lane).
+template <int V>
+__global__ void __launch_bounds__(256) k11_ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float eps,
+                                                           __half* __restrict__ h1p, __half* __restrict__ h2p,
+                                                           float* __restrict__ inv_scale, int rows) {
+  constexpr int K = 128 * V;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * K);
+  float4 v[V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = __ldg(xr + lane + 32 * i);
+    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.0f / K);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    sq += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq * (1.0f / K) + eps);
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
+    v[i].x = (v[i].x - mean) * rstd * g.x + bt.x;
+    v[i].y = (v[i].y - mean) * rstd * g.y + bt.y;
+    v[i].z = (v[i].z - mean) * rstd * g.z + bt.z;
+    v[i].w = (v[i].w - mean) * rstd * g.w + bt.w;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  int ex = 0;
+  if (mx > 0.f) frexpf(mx, &ex);
+  ex = max(-100, min(100, ex));
+  const float scale = exp2f(static_cast<float>(14 - ex));
+  if (lane == 0) {
+    inv_scale[row] = exp2f(static_cast<float>(ex - 14));
+    if (!(mx <= 3.0e38f) || !(sq <= 3.0e38f)) g_k11_flag = 1;
+  }
+  uint2* o1 = reinterpret_cast<uint2*>(h1p + static_cast<size_t>(row) * K);
+  uint2* o2 = reinterpret_cast<uint2*>(h2p + static_cast<size_t>(row) * K);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x * scale, b = v[i].y * scale, c = v[i].z * scale, d = v[i].w * scale;
+    const __half2 p0 = __floats2half2_rn(a, b), p1 = __floats2half2_rn(c, d);
+    const float2 f0 = __half22float2(p0), f1 = __half22float2(p1);
+    const __half2 q0 = __floats2half2_rn(a - f0.x, b - f0.y), q1 = __floats2half2_rn(c - f1.x, d - f1.y);
+    o1[lane + 32 * i] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+    o2[lane + 32 * i] = make_uint2(*reinterpret_cast<const uint32_t*>(&q0), *reinterpret_cast<const uint32_t*>(&q1));
+  }
+}
+
 struct LArgs {
   const float* inv_a;   // [M]
   const float* inv_w;   // [N]
-  const float* bias;    // [N] or nullptr
-  float* out;           // [M, N] (split_k == 1) or partials [split_k, M, N]
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // [M, N] or nullptr: out = residual + act(...)
+  float* out;             // [M, N]
   int M, N, K, act, split_k, kc_per_split;
 };
 
@@ -160,45 +225,117 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant
     // epilogue: warp w owns TMEM lanes 32 (w % 4) .. + 31 = rows m0 + 32 (w % 4) + lane
     const int quarter = warp & 3;
     const int row = m0 + quarter * 32 + lane;
-    const float ia = row < a.M ? a.inv_a[row] : 0.f;
+    const bool row_ok = row < a.M;
+    const float ia = row_ok ? a.inv_a[row] : 0.f;
     mbar_wait_bounded(done, 0, &g_k11_flag, 18);
     tc_fence_after();
-    float* orow = a.out + (static_cast<size_t>(z) * a.M + (row < a.M ? row : 0)) * a.N;
-    const bool final_out = a.split_k == 1;
+    const size_t rofs = static_cast<size_t>(row_ok ? row : 0) * a.N;
+    auto finish = [&](float4 o, int n) {   // + bias, activation, + residual -> out
+      if (a.bias) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        o.x += b.x;
+        o.y += b.y;
+        o.z += b.z;
+        o.w += b.w;
+      }
+      o.x = act_apply(o.x, a.act);
+      o.y = act_apply(o.y, a.act);
+      o.z = act_apply(o.z, a.act);
+      o.w = act_apply(o.w, a.act);
+      if (a.residual) {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + rofs + n));
+        o.x += r.x;
+        o.y += r.y;
+        o.z += r.z;
+        o.w += r.w;
+      }
+      *reinterpret_cast<float4*>(a.out + rofs + n) = o;
+    };
+    // split-K: the K slices of one output tile are the CTAs of a cluster (rank = slice).  Each parks its scaled fp32
+    // tile in its own shared memory (the operand ring is dead by now); after a cluster barrier rank r adds rows
+    // [128 r / split_k, 128 (r + 1) / split_k) of all slices in ascending slice order over DSMEM and finishes them
+    // with coalesced stores.  No partials in global memory, no second launch, bit-reproducible.
+    constexpr int PITCH = BN + 4;   // floats per parked row: row-per-lane 16-byte writes without extra bank conflicts
+    float* park = reinterpret_cast<float*>(stage);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[2][16];
       tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v[0]);
       tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0 + 16, v[1]);
       tmem_ld_wait();
-      if (row < a.M) {
 #pragma unroll
-        for (int g = 0; g < 2; ++g)
+      for (int g = 0; g < 2; ++g)
 #pragma unroll
-          for (int q = 0; q < 16; q += 4) {
-            const int n = n0 + c0 + 16 * g + q;
-            if (n < a.N) {  // N % 4 == 0
-              const float4 iw = __ldg(reinterpret_cast<const float4*>(a.inv_w + n));
-              float4 o = make_float4(__uint_as_float(v[g][q]) * (ia * iw.x), __uint_as_float(v[g][q + 1]) * (ia * iw.y),
-                                     __uint_as_float(v[g][q + 2]) * (ia * iw.z), __uint_as_float(v[g][q + 3]) * (ia * iw.w));
-              if (final_out) {
-                if (a.bias) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n));
-                  o.x += b.x;
-                  o.y += b.y;
-                  o.z += b.z;
-                  o.w += b.w;
-                }
-                o.x = act_apply(o.x, a.act);
-                o.y = act_apply(o.y, a.act);
-                o.z = act_apply(o.z, a.act);
-                o.w = act_apply(o.w, a.act);
-              }
-              *reinterpret_cast<float4*>(orow + n) = o;
+        for (int q = 0; q < 16; q += 4) {
+          const int cl = c0 + 16 * g + q, n = n0 + cl;
+          float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row_ok && n < a.N) {  // N % 4 == 0
+            const float4 iw = __ldg(reinterpret_cast<const float4*>(a.inv_w + n));
+            o = make_float4(__uint_as_float(v[g][q]) * (ia * iw.x), __uint_as_float(v[g][q + 1]) * (ia * iw.y),
+                            __uint_as_float(v[g][q + 2]) * (ia * iw.z), __uint_as_float(v[g][q + 3]) * (ia * iw.w));
+            if (a.split_k == 1) finish(o, n);
+          }
+          if (a.split_k > 1) *reinterpret_cast<float4*>(park + (quarter * 32 + lane) * PITCH + cl) = o;
+        }
+    }
+  }
+  if (a.split_k > 1) {
+    // (all 192 threads of every CTA of the cluster take part in the barriers)
+    cluster_barrier();   // every slice is parked (release / acquire at cluster scope)
+    if (warp >= 2) {
+      constexpr int PITCH = BN + 4;
+      float* park = reinterpret_cast<float*>(stage);
+      const int rows_per = 128 / a.split_k;          // split_k is a power of two <= 16
+      const int r_lo = z * rows_per;
+      const int t = tid - 64;                        // 0..127
+      constexpr int C4 = BN / 4;
+      const uint32_t park_s = smem_u32(park);
+      for (int idx = t; idx < rows_per * C4; idx += 128) {
+        const int rl = idx / C4, c4 = idx - rl * C4;
+        const int rr = r_lo + rl, n = n0 + 4 * c4;
+        if (m0 + rr < a.M && n < a.N) {
+          const uint32_t off = park_s + static_cast<uint32_t>((rr * PITCH + 4 * c4) * 4);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int zz = 0; zz < a.split_k; ++zz) {
+            uint32_t remote;
+            float4 p;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(off), "r"(zz));
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w)
+                         : "r"(remote));
+            if (zz == 0) acc = p;
+            else {
+              acc.x += p.x;
+              acc.y += p.y;
+              acc.z += p.z;
+              acc.w += p.w;
             }
           }
+          // (finish() addresses rows through rofs of THIS thread's epilogue row: use explicit offsets here)
+          const size_t ro = static_cast<size_t>(m0 + rr) * a.N;
+          if (a.bias) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+            acc.x += b.x;
+            acc.y += b.y;
+            acc.z += b.z;
+            acc.w += b.w;
+          }
+          acc.x = act_apply(acc.x, a.act);
+          acc.y = act_apply(acc.y, a.act);
+          acc.z = act_apply(acc.z, a.act);
+          acc.w = act_apply(acc.w, a.act);
+          if (a.residual) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(a.residual + ro + n));
+            acc.x += r.x;
+            acc.y += r.y;
+            acc.z += r.z;
+            acc.w += r.w;
+          }
+          *reinterpret_cast<float4*>(a.out + ro + n) = acc;
+        }
       }
     }
+    cluster_barrier();   // nobody leaves while a peer may still read its parked tile
   }
   tc_fence_before();
   __syncthreads();
@@ -208,43 +345,27 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant
   }
 }
 
-// out = act( sum_z partial[z] + bias ), z in ascending order
-__global__ void __launch_bounds__(256) k11_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ bias,
-                                                         float* __restrict__ out, int64_t mn4, int n4, int split_k, int act) {
-  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= mn4) return;
-  float4 s = __ldg(reinterpret_cast<const float4*>(partial) + i);
-  for (int z = 1; z < split_k; ++z) {
-    const float4 p = __ldg(reinterpret_cast<const float4*>(partial) + static_cast<int64_t>(z) * mn4 + i);
-    s.x += p.x;
-    s.y += p.y;
-    s.z += p.z;
-    s.w += p.w;
-  }
-  if (bias) {
-    const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (i % n4));
-    s.x += b.x;
-    s.y += b.y;
-    s.z += b.z;
-    s.w += b.w;
-  }
-  s.x = act_apply(s.x, act);
-  s.y = act_apply(s.y, act);
-  s.z = act_apply(s.z, act);
-  s.w = act_apply(s.w, act);
-  reinterpret_cast<float4*>(out)[i] = s;
-}
-
 template <int BN>
 int launch_k11(const CUtensorMap* tm, const LArgs& a, cudaStream_t st) {
   constexpr int STAGE = 2 * L_A_PLANE + 2 * BN * 128;
   constexpr int STAGES = (200 * 1024) / STAGE;
   constexpr int SMEM = 1024 + STAGES * STAGE + 256;
   static_assert(SMEM <= 227 * 1024, "K11 shared memory");
+  static_assert(128 * (BN + 4) * 4 <= STAGES * STAGE, "the parked split-K tile fits the operand ring");
   FD_CUDA_OK(cudaFuncSetAttribute(k11_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-  dim3 grid((a.M + 127) / 128, (a.N + BN - 1) / BN, a.split_k);
-  k11_gemm_kernel<BN><<<grid, L_THREADS, SMEM, st>>>(tm[0], tm[1], tm[2], tm[3], a);
-  FD_CUDA_OK(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((a.M + 127) / 128, (a.N + BN - 1) / BN, a.split_k);
+  cfg.blockDim = dim3(L_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = static_cast<unsigned>(a.split_k);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k11_gemm_kernel<BN>, tm[0], tm[1], tm[2], tm[3], a));
   return FD_OK;
 }
 
@@ -276,24 +397,53 @@ extern "C" int fd_linear_x3_split(const float* x_dev, int rows, int K, void* ope
   return FD_OK;
 }
 
+extern "C" int fd_linear_x3_split_ln(const float* x_dev, int rows, int K, const float* gamma_dev, const float* beta_dev,
+                                     float eps, void* operand_dev, int64_t operand_bytes, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(x_dev && gamma_dev && beta_dev && operand_dev, "fd_linear_x3_split_ln: NULL pointer");
+  FD_REQUIRE(rows > 0 && K > 0 && K % 128 == 0 && K <= 2048,
+             "fd_linear_x3_split_ln: need rows > 0 and K a multiple of 128 up to 2048 (rows=%d, K=%d)", rows, K);
+  FD_REQUIRE(operand_bytes >= fd_linear_x3_operand_bytes(rows, K), "fd_linear_x3_split_ln: operand buffer too small");
+  FD_REQUIRE(reinterpret_cast<uintptr_t>(x_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma_dev) % 16 == 0 &&
+                 reinterpret_cast<uintptr_t>(beta_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(operand_dev) % 256 == 0,
+             "fd_linear_x3_split_ln: x / gamma / beta must be 16-byte and the operand buffer 256-byte aligned");
+  int rc = check_device();
+  if (rc != FD_OK) return rc;
+  const int64_t plane = (static_cast<int64_t>(rows) * K * 2 + 255) / 256 * 256;
+  uint8_t* base = static_cast<uint8_t*>(operand_dev);
+  __half* h1 = reinterpret_cast<__half*>(base);
+  __half* h2 = reinterpret_cast<__half*>(base + plane);
+  float* inv = reinterpret_cast<float*>(base + 2 * plane);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (rows + 7) / 8;
+  switch (K / 128) {
+#define FD_LN_CASE(V) case V: k11_ln_split_kernel<V><<<grid, 256, 0, st>>>(x_dev, gamma_dev, beta_dev, eps, h1, h2, inv, rows); break;
+    FD_LN_CASE(1) FD_LN_CASE(2) FD_LN_CASE(3) FD_LN_CASE(4) FD_LN_CASE(5) FD_LN_CASE(6) FD_LN_CASE(7) FD_LN_CASE(8)
+    FD_LN_CASE(9) FD_LN_CASE(10) FD_LN_CASE(11) FD_LN_CASE(12) FD_LN_CASE(13) FD_LN_CASE(14) FD_LN_CASE(15) FD_LN_CASE(16)
+#undef FD_LN_CASE
+  }
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
+}
+
 extern "C" int fd_linear_x3(const void* act_operand_dev, int M, const void* weight_operand_dev, int N, int K,
-                            const float* bias_dev, int act, float* out_dev, float* partial_dev, int split_k,
+                            const float* bias_dev, int act, const float* residual_dev, float* out_dev, int split_k,
                             void* stream) {
   using namespace fd;
   FD_REQUIRE(act_operand_dev && weight_operand_dev && out_dev, "fd_linear_x3: NULL pointer");
   FD_REQUIRE(M > 0 && N > 0 && K > 0, "fd_linear_x3: non-positive shape");
   FD_REQUIRE(K % L_KC == 0 && N % 4 == 0, "fd_linear_x3: need K %% 64 == 0 and N %% 4 == 0 (K=%d, N=%d)", K, N);
   FD_REQUIRE(act >= 0 && act <= FD_LINEAR_ACT_GELU, "fd_linear_x3: unknown activation %d", act);
-  FD_REQUIRE(split_k >= 1 && split_k <= 16 && (split_k == 1 || partial_dev), "fd_linear_x3: split_k=%d needs a partial buffer",
+  FD_REQUIRE(split_k == 1 || split_k == 2 || split_k == 4 || split_k == 8, "fd_linear_x3: split_k=%d not in {1, 2, 4, 8}",
              split_k);
   FD_REQUIRE(reinterpret_cast<uintptr_t>(out_dev) % 16 == 0 && (!bias_dev || reinterpret_cast<uintptr_t>(bias_dev) % 16 == 0) &&
-                 (!partial_dev || reinterpret_cast<uintptr_t>(partial_dev) % 16 == 0),
-             "fd_linear_x3: out / bias / partial must be 16-byte aligned");
+                 (!residual_dev || reinterpret_cast<uintptr_t>(residual_dev) % 16 == 0),
+             "fd_linear_x3: out / bias / residual must be 16-byte aligned");
   int rc = check_device();
   if (rc != FD_OK) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int num_kc = K / L_KC;
-  if (split_k > num_kc) split_k = num_kc;
+  while (split_k > num_kc) split_k >>= 1;
   const int bn = N >= 2048 || (N % 128 == 0 && static_cast<int64_t>((M + 127) / 128) * (N / 128) * split_k >= 96) ? 128 : 64;
   const uint8_t* ab = static_cast<const uint8_t*>(act_operand_dev);
   const uint8_t* wb = static_cast<const uint8_t*>(weight_operand_dev);
@@ -313,22 +463,15 @@ extern "C" int fd_linear_x3(const void* act_operand_dev, int M, const void* weig
   a.inv_a = reinterpret_cast<const float*>(ab + 2 * a_plane);
   a.inv_w = reinterpret_cast<const float*>(wb + 2 * w_plane);
   a.bias = bias_dev;
-  a.out = split_k == 1 ? out_dev : partial_dev;
+  a.residual = residual_dev;
+  a.out = out_dev;
   a.M = M;
   a.N = N;
   a.K = K;
   a.act = act;
   a.split_k = split_k;
   a.kc_per_split = (num_kc + split_k - 1) / split_k;
-  rc = bn == 128 ? launch_k11<128>(tm, a, st) : launch_k11<64>(tm, a, st);
-  if (rc != FD_OK) return rc;
-  if (split_k > 1) {
-    const int64_t mn4 = static_cast<int64_t>(M) * N / 4;
-    k11_reduce_kernel<<<static_cast<unsigned>((mn4 + 255) / 256), 256, 0, st>>>(partial_dev, bias_dev, out_dev, mn4, N / 4,
-                                                                               split_k, act);
-    FD_CUDA_OK(cudaGetLastError());
-  }
-  return FD_OK;
+  return bn == 128 ? launch_k11<128>(tm, a, st) : launch_k11<64>(tm, a, st);
 }
 
 // development aid / health check: 1 = a non-finite operand was split since the last call, >= 16 = a pipeline wait

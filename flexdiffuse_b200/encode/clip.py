@@ -5,7 +5,8 @@ reference's signatures and numerics.  The weights, embeddings, layer norms and t
 core stay transformers' / PyTorch's; on an sm_100 device every Linear of the two encoders
 (q / k / v / out_proj, fc1 + activation, fc2 -- 99 % of the towers' arithmetic) runs on K11
 `fd_linear_x3`, an fp32-accurate tcgen05 GEMM, and `visual_projection` on
-K1P.  Each tower forward is captured once per input shape and replayed as a CUDA graph.
+K1P; the 257- / 77-token attention core is K12 (exact fp32).  Each tower forward is captured once per
+input shape and replayed as a CUDA graph.
 '''
 from __future__ import annotations
 
@@ -21,9 +22,9 @@ _CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
 _CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
 
 
-def preprocess(image: Any) -> torch.Tensor:
-    '''PIL image -> [1,3,h,w] float32 in [-1,1]; the longer side becomes 512, the
-    shorter one is scaled with it and floored to a multiple of 64 (clip.py:24-39).'''
+def _resized_rgb(image: Any) -> np.ndarray:
+    '''The LANCZOS resize of clip.py:24-36: the longer side becomes 512, the shorter one is scaled with
+    it and floored to a multiple of 64; uint8 [h, w, 3].'''
     from PIL.Image import LANCZOS
     w, h = image.size
     if h == w:
@@ -32,8 +33,13 @@ def preprocess(image: Any) -> torch.Tensor:
         w, h = (int(w / (h / MAX_SINGLE_DIM)) // 64) * 64, MAX_SINGLE_DIM
     else:
         h, w = (int(h / (w / MAX_SINGLE_DIM)) // 64) * 64, MAX_SINGLE_DIM
-    arr = np.array(image.resize((w, h), resample=LANCZOS).convert('RGB'))
-    arr = arr.astype(np.float32) / 255.0
+    return np.array(image.resize((w, h), resample=LANCZOS).convert('RGB'))
+
+
+def preprocess(image: Any) -> torch.Tensor:
+    '''PIL image -> [1,3,h,w] float32 in [-1,1]; the longer side becomes 512, the
+    shorter one is scaled with it and floored to a multiple of 64 (clip.py:24-39).'''
+    arr = _resized_rgb(image).astype(np.float32) / 255.0
     return 2.0 * torch.from_numpy(arr[None].transpose(0, 3, 1, 2)) - 1.0
 
 
@@ -86,31 +92,67 @@ def _x3_ok(encoder, hidden: torch.Tensor) -> bool:
             and l0.mlp.fc1.weight.dtype == torch.float32)
 
 
+_qkv_cache = {}   # (q, k, v weight storage + version) -> (concatenated weight, bias, the three source weights)
+
+
+def _qkv_weight(at):
+    '''[3C, C] weight and [3C] bias of one attention block, so q, k and v are ONE K11 GEMM; rebuilt when any
+    of the three projections changes (the cache keeps the sources alive: no address reuse under a stale entry).'''
+    ws = (at.q_proj.weight, at.k_proj.weight, at.v_proj.weight)
+    bs = (at.q_proj.bias, at.k_proj.bias, at.v_proj.bias)
+    key = tuple((w.data_ptr(), w._version) for w in ws) + tuple((b.data_ptr(), b._version) for b in bs)
+    ent = _qkv_cache.get(key)
+    if ent is None:
+        if len(_qkv_cache) > 256:
+            _qkv_cache.clear()
+        ent = (torch.cat([w.detach() for w in ws]).contiguous(), torch.cat([b.detach() for b in bs]).contiguous(), ws, bs)
+        _qkv_cache[key] = ent
+    return ent[0], ent[1]
+
+
 def _x3_encoder(encoder, hidden: torch.Tensor, causal: bool) -> torch.Tensor:
     '''transformers' CLIPEncoder.forward (pre-LN blocks: `x + attn(ln1(x))`, `x + mlp(ln2(x))`) with every
-    Linear on K11.  One split of the block input feeds q, k and v; fc1's bias and activation ride in
-    the GEMM epilogue; the attention core is torch SDPA in fp32 (causal for the text tower, as
-    CLIPTextTransformer builds its mask).'''
-    from torch.nn.functional import scaled_dot_product_attention as sdpa
+    Linear on K11 and the attention core on K12.  The two LayerNorms are fused into the operand split of the
+    GEMM they feed, q, k and v are one GEMM against the concatenated weights, fc1's bias and activation and both
+    residual adds ride in GEMM epilogues: 7 launches per block.  The text tower is causal, as CLIPTextTransformer
+    builds its mask.'''
     from .. import _native
     B, T, C = hidden.shape
+    hidden = hidden.reshape(B * T, C)
+    M = B * T
+
+    def ln_operand(ln, x):   # operand buffer of ln(x): fused LayerNorm + split where K11 has the kernel
+        if C % 128 == 0 and C <= 2048 and ln.elementwise_affine and ln.bias is not None:
+            return _native.x3_split_ln(x, ln.weight, ln.bias, ln.eps)
+        return _native.x3_split(ln(x))
+
     for layer in encoder.layers:
         at, mlp = layer.self_attn, layer.mlp
         H = at.num_heads
-        x = layer.layer_norm1(hidden).reshape(B * T, C)
-        op = _native.x3_split(x)
-        q = _native.linear_x3(x, at.q_proj.weight, at.q_proj.bias, operand=op)
-        k = _native.linear_x3(x, at.k_proj.weight, at.k_proj.bias, operand=op)
-        v = _native.linear_x3(x, at.v_proj.weight, at.v_proj.bias, operand=op)
-        q, k, v = (t.view(B, T, H, C // H).transpose(1, 2) for t in (q, k, v))
-        o = sdpa(q, k, v, is_causal=causal, scale=at.scale).transpose(1, 2).reshape(B * T, C)
-        hidden = hidden + _native.linear_x3(o, at.out_proj.weight, at.out_proj.bias).view(B, T, C)
-        x = layer.layer_norm2(hidden).reshape(B * T, C)
+        op = ln_operand(layer.layer_norm1, hidden)
+        if at.q_proj.bias is not None and at.k_proj.bias is not None and at.v_proj.bias is not None:
+            w_qkv, b_qkv = _qkv_weight(at)
+            qkv = _native.linear_x3(None, w_qkv, b_qkv, operand=op, rows=M).view(B, T, 3 * C)
+            q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        else:
+            q, k, v = (_native.linear_x3(None, p.weight, p.bias, operand=op, rows=M).view(B, T, C)
+                       for p in (at.q_proj, at.k_proj, at.v_proj))
+        if _native.attention_f32_supported(T, C // H):
+            o = _native.attention_f32(q, k, v, H, at.scale, causal).view(M, C)
+        else:  # sequences the K12 kernel does not serve: torch's fp32 SDPA
+            from torch.nn.functional import scaled_dot_product_attention as sdpa
+            q, k, v = (t.reshape(B, T, H, C // H).transpose(1, 2) for t in (q, k, v))
+            o = sdpa(q, k, v, is_causal=causal, scale=at.scale).transpose(1, 2).reshape(M, C)
+        hidden = _native.linear_x3(o, at.out_proj.weight, at.out_proj.bias, residual=hidden)   # x + attn(ln1(x))
+        op = ln_operand(layer.layer_norm2, hidden)
         act = _X3_ACTS.get(getattr(mlp.config, 'hidden_act', None), 0)
-        h = _native.linear_x3(x, mlp.fc1.weight, mlp.fc1.bias, act=act)
+        h = _native.linear_x3(None, mlp.fc1.weight, mlp.fc1.bias, act=act, operand=op, rows=M)
         if not act:
             h = mlp.activation_fn(h)
-        hidden = hidden + _native.linear_x3(h, mlp.fc2.weight, mlp.fc2.bias).view(B, T, C)
+        hidden = _native.linear_x3(h, mlp.fc2.weight, mlp.fc2.bias, residual=hidden)           # x + mlp(ln2(x))
+    return hidden.view(B, T, C)
+
+
     return hidden
 
 
@@ -173,12 +215,15 @@ class CLIPEncoder():
         from torchvision.transforms.functional import (InterpolationMode,
                                                        center_crop, normalize,
                                                        resize)
+        dev = self.clip.device
+        # (crop / antialiased bicubic resize stay on the CPU like the reference: torchvision's CUDA resize differs
+        # from its CPU one by ~1e-4 in the pixels, 3e-4 in the embeddings -- measured, not worth 0.4 ms)
         x = preprocess(image)
         side = min(x.shape[-2:])
         x = center_crop(x, [side, side])
         x = resize(x, [CLIP_IMAGE_SIZE, CLIP_IMAGE_SIZE],
                    interpolation=InterpolationMode.BICUBIC, antialias=True)
-        x = normalize(x, list(_CLIP_MEAN), list(_CLIP_STD)).to(self.clip.device)
+        x = normalize(x, list(_CLIP_MEAN), list(_CLIP_STD)).to(dev)
         return self._run('image', self._vision, x)
 
     def _vision(self, x: torch.Tensor) -> torch.Tensor:

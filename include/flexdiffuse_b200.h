@@ -223,19 +223,37 @@ int fd_linear_x3_split(const float* x_dev,      /* [rows, K] fp32 row-major, K %
                        int rows, int K,
                        void* operand_dev,       /* >= fd_linear_x3_operand_bytes, 256-B aligned  */
                        int64_t operand_bytes, void* stream);
+/* LayerNorm fused with the split: operand of y = LayerNorm(x) * gamma + beta (y itself is never written). */
+int fd_linear_x3_split_ln(const float* x_dev, int rows, int K,   /* K % 128 == 0, K <= 2048             */
+                          const float* gamma_dev, const float* beta_dev, float eps,
+                          void* operand_dev, int64_t operand_bytes, void* stream);
 int fd_linear_x3(const void* act_operand_dev,   /* split [M, K]                                  */
                  int M,
                  const void* weight_operand_dev,/* split [N, K]                                  */
                  int N, int K,                  /* N % 4 == 0                                    */
                  const float* bias_dev,         /* [N] fp32 or NULL                              */
                  int act,                       /* FD_LINEAR_ACT_*                               */
+                 const float* residual_dev,     /* [M, N] fp32 added after the activation, or NULL */
                  float* out_dev,                /* [M, N] fp32                                   */
-                 float* partial_dev,            /* [split_k, M, N] fp32 scratch, NULL if split_k == 1 */
-                 int split_k,                   /* 1..16: K is cut into this many slices, reduced in a fixed order */
+                 int split_k,                   /* 1, 2, 4 or 8: K is cut into this many slices, one CTA of a thread-block
+                                                   cluster each; the slices are added in ascending order over DSMEM
+                                                   (bit-reproducible, no scratch in global memory)                  */
                  void* stream);
 /* 1 if a non-finite operand was split since the last call, >= 16 if a pipeline wait gave up;
  * clears the flag; synchronises the device.                                                 */
 int fd_linear_x3_flag(void);
+
+/* ---- K12: exact-fp32 attention core for the CLIP towers' short sequences ---------------- *
+ * Replaces the fp32 attention inside transformers' CLIPAttention (reached from encode/clip.py:57-65
+ * and :86-100): out[b,t,h,:] = softmax_j(scale <q[b,t,h,:], k[b,j,h,:]> [+ causal mask]) . v[b,:,h,:].
+ * q / k / v are [B * T] rows of `row_stride` floats with head h at column h * d (e.g. the three
+ * column blocks of one fused q|k|v GEMM output); out is [B * T, H * d] contiguous.             */
+int fd_attention_f32(const float* q_dev, const float* k_dev, const float* v_dev,
+                     int64_t row_stride,            /* floats between consecutive tokens          */
+                     float* out_dev,
+                     int B, int T,                  /* T <= 288                                   */
+                     int H, int d,                  /* d % 4 == 0, d <= 128                       */
+                     float scale, int causal, void* stream);
 
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
  * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'
