@@ -1290,9 +1290,11 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
   } else if (warp == 1) {
     // ================================================================ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(UMMA_F16, 128, KB_NTXT, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc(UMMA_F16, 128, KB_NTXT, 0, 0);
+      constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, 128, NPAD, 0, 0);   // a CTA's last batch may hold one prompt: N = 80
       int g = 0;
       for (int b = 0; b < my_batches; ++b) {
+        const uint32_t idesc = (p_hi - (p_lo + b * KB_NP)) >= KB_NP ? idesc2 : idesc1;
         if (b > 0) mbar_wait_backoff(&sm.acc_free, (b - 1) & 1);  // the tail has drained batch b - 1
         tc_fence_after();
         for (int kc = 0; kc < num_kc; ++kc, ++g) {
@@ -1374,11 +1376,9 @@ k1b_sim_blend_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_con
       for (int j = 0; j < KB_ITEMS; ++j) {
         const int f = tt + j * KB_FEED_THREADS;
         const int row = f >> 2;
-        float4 r0 = rr0[j], r1 = rr1[j];
-        if (row >= NPAD && n_here != KB_NP) {  // rows T..79 arrive zero-filled by TMA; a missing prompt is not loaded
-          r0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          r1 = r0;
-        }
+        // rows T..79 arrive zero-filled by TMA; a missing second prompt is neither loaded nor multiplied (N = 80 MMAs)
+        if (row >= NPAD && n_here != KB_NP) continue;
+        const float4 r0 = rr0[j], r1 = rr1[j];
         const float x[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
         uint32_t ph[4], pl[4];
         float am = 0.f;
