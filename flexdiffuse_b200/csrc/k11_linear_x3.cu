@@ -149,8 +149,7 @@ struct LArgs {
 
 template <int BN>
 __global__ void __launch_bounds__(L_THREADS, 1)
-k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_a2,
-                const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2, const LArgs a) {
+k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const LArgs a) {
   constexpr int W_PLANE = BN * 128;
   constexpr int STAGE = 2 * L_A_PLANE + 2 * W_PLANE;
   constexpr int STAGES = (200 * 1024) / STAGE;   // BN 128: 3 stages of 64 KB, BN 64: 4 of 48 KB
@@ -166,12 +165,10 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant
   const int kc0 = z * a.kc_per_split;
   const int num_kc = min(a.kc_per_split, a.K / L_KC - kc0);
   if (tid == 0) {
-    tma_prefetch_desc(&tm_a1);
-    tma_prefetch_desc(&tm_a2);
-    tma_prefetch_desc(&tm_w1);
-    tma_prefetch_desc(&tm_w2);
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], 2);   // one arrival (+ its bytes) from each of the two producer threads
       mbar_init(&empty[s], 1);
     }
     mbar_init(done, 1);
@@ -186,20 +183,29 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a1, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // Two producer threads, ONE box each per K chunk: a thread issues at most one TMA box per ~340 cycles whatever its size
+  // (profiles/microbench/tma_rate_all.cu), so both planes of an operand travel as one 3-D box {64, rows, 2 planes} and the
+  // activation / weight boxes come from different warps (warp 0 and, while it has nothing else to do, epilogue warp 2).
+  if (warp == 0 || warp == 2) {
     if (elect_one()) {
+      const bool is_w = warp == 2;
       for (int i = 0; i < num_kc; ++i) {
         const int s = i % STAGES;
         mbar_wait_bounded(&empty[s], ((i / STAGES) & 1) ^ 1, &g_k11_flag, 16);
-        mbar_expect_tx(&full[s], STAGE);
         uint8_t* st = stage + s * STAGE;
         const int k = (kc0 + i) * L_KC;
-        tma_load_2d(st, &tm_a1, &full[s], k, m0);
-        tma_load_2d(st + L_A_PLANE, &tm_a2, &full[s], k, m0);
-        tma_load_2d(st + 2 * L_A_PLANE, &tm_w1, &full[s], k, n0);
-        tma_load_2d(st + 2 * L_A_PLANE + W_PLANE, &tm_w2, &full[s], k, n0);
+        if (is_w) {
+          mbar_expect_tx(&full[s], 2 * W_PLANE);
+          tma_load_3d(st + 2 * L_A_PLANE, &tm_w, &full[s], k, n0, 0);
+        } else {
+          mbar_expect_tx(&full[s], 2 * L_A_PLANE);
+          tma_load_3d(st, &tm_a, &full[s], k, m0, 0);
+        }
       }
     }
+    __syncwarp();
+  }
+  if (warp == 0) {
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc(UMMA_F16, 128, BN, 0, 0);
@@ -365,7 +371,7 @@ int launch_k11(const CUtensorMap* tm, const LArgs& a, cudaStream_t st) {
   attr[0].val.clusterDim.z = static_cast<unsigned>(a.split_k);
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k11_gemm_kernel<BN>, tm[0], tm[1], tm[2], tm[3], a));
+  FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k11_gemm_kernel<BN>, tm[0], tm[1], a));
   return FD_OK;
 }
 
@@ -449,14 +455,15 @@ extern "C" int fd_linear_x3(const void* act_operand_dev, int M, const void* weig
   const uint8_t* wb = static_cast<const uint8_t*>(weight_operand_dev);
   const int64_t a_plane = (static_cast<int64_t>(M) * K * 2 + 255) / 256 * 256;
   const int64_t w_plane = (static_cast<int64_t>(N) * K * 2 + 255) / 256 * 256;
-  CUtensorMap tm[4];
-  for (int which = 0; which < 4; ++which) {
-    const bool is_w = which >= 2;
-    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(is_w ? N : M)};
-    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t box[2] = {L_KC, static_cast<uint32_t>(is_w ? bn : 128)};
-    const void* p = is_w ? static_cast<const void*>(wb + (which & 1) * w_plane) : static_cast<const void*>(ab + (which & 1) * a_plane);
-    rc = encode_tmap(&tm[which], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, p, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tm[2];
+  for (int which = 0; which < 2; ++which) {
+    // {K, rows, 2 planes}: one box {64, tile rows, 2} brings the h1 and h2 tiles of a K chunk, back to back in shared memory
+    const bool is_w = which == 1;
+    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(is_w ? N : M), 2};
+    uint64_t strides[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(is_w ? w_plane : a_plane)};
+    uint32_t box[3] = {L_KC, static_cast<uint32_t>(is_w ? bn : 128), 2};
+    rc = encode_tmap(&tm[which], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, is_w ? static_cast<const void*>(wb) : ab, dims, strides, box,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;
   }
   LArgs a;

@@ -56,5 +56,28 @@ _native.add_layernorm(rn(133, 640).bfloat16(), rn(133, 640).bfloat16(), torch.on
 b = _native.EntityBox()
 b.ox, b.oy, b.sx, b.sy, b.blend = 2, 3, 8, 20, 0.8
 _native.composite_eps(rn(3, 4, 16, 16).bfloat16(), [b])
+# K1B (batched path: 5 prompts -> a CTA with one full and one single-prompt batch), K1P, K3F, K10, K11 (split-K cluster, LN split), K12
+_native.lib().fd_debug_set_k1_fast(1, 1)
+p = _native.TweenParams()
+p.threshold_floor = p.threshold_mult = p.max_guidance = p.clustered = 0.5
+p.header_max, p.align_mode, p.mapping_reuse = 0.15, 1, 1
+_native.sim_blend(rn(5, 77, 768), rn(1, 257, 768), [p, p], torch.linspace(0, 0.5, 77)[None].repeat(2, 1).to(dev))
+_native.lib().fd_debug_set_k1_fast(1, 64)
+_native.visual_projection(rn(130, 192), rn(260, 192) * 0.03)
+for C, nq in ((320, 200), (640, 130)):
+    d_kv = rn(160, 2 * C).bfloat16()
+    _native.cross_attn_fused(rn(2, nq, C).bfloat16(), (rn(C, C) * C ** -0.5).bfloat16(), d_kv, 0, C,
+                             torch.tensor([0, 1], dtype=torch.int32, device=dev), (rn(C, C) * C ** -0.5).bfloat16(),
+                             rn(C).bfloat16(), 8, 77, 80, (C // 8) ** -0.5)
+_native.image_tail_u8(rn(1, 3, 24, 24))
+xa, wa, ba = rn(130, 256), rn(260, 256) * 0.05, rn(260)
+op = _native.x3_split_ln(xa, torch.ones(256, device=dev), torch.zeros(256, device=dev), 1e-5)
+for sk in (1, 2, 4):
+    _native.linear_x3(None, wa, ba, act=1, operand=op, rows=130, residual=rn(130, 260), split_k=sk)
+_native.linear_x3(xa, wa, ba)
+qkv = rn(2, 77, 3 * 128)
+_native.attention_f32(qkv[..., :128], qkv[..., 128:256], qkv[..., 256:], 2, 0.125, True)
+qkv = rn(1, 257, 3 * 64)
+_native.attention_f32(qkv[..., :64], qkv[..., 64:128], qkv[..., 128:], 4, 0.25, False)
 torch.cuda.synchronize()
 print('all kernels launched once')
