@@ -14,7 +14,7 @@
 //   k11_split_rows_kernel   fp32 rows -> h1 / h2 planes + the row's inverse scale (weights once per
 //                           version, activations once per call; one warp per row)
 //   k11_gemm_kernel<BN>     both operands by TMA (SWIZZLE_128B, K chunks of 64, multi-stage ring),
-//                           warp 0 producer, warp 1 MMA issuer (M128 N=BN K16, three products per k-step),
+//                           warps 0 / 2 producers, warp 1 MMA issuer (per k-step h1 x [w1; w2] as one M128 N=2BN MMA, then h2 x w1),
 //                           warps 2-5 epilogue: TMEM -> x inv_a[row] x inv_w[col] (+ bias, activation, residual) ->
 //                           fp32 global; with split-K the last CTA of a tile to finish adds the slices in ascending order
 //   k11_ln_split_kernel     LayerNorm fused with the split (the towers' pre-LN blocks feed every q|k|v and fc1 GEMM)
@@ -175,7 +175,7 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     fence_mbar_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -208,20 +208,23 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   if (warp == 0) {
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc(UMMA_F16, 128, BN, 0, 0);
+      // two MMAs per k-step instead of three: h1 against BOTH weight planes at once (their tiles are adjacent in shared
+      // memory: one B operand of 2 BN rows -> accumulators D1 | D2 side by side), then h2 against w1 into D1.  The A tile is
+      // read twice instead of three times -- the kernel is bound by shared-memory bandwidth (SS-mode MMAs at N <= 128 read
+      // as many bytes as the tensor pipe can take) and by the single-thread issue rate at N = 64.
+      constexpr uint32_t idesc2 = umma_idesc(UMMA_F16, 128, 2 * BN, 0, 0);
+      constexpr uint32_t idesc1 = umma_idesc(UMMA_F16, 128, BN, 0, 0);
       for (int i = 0; i < num_kc; ++i) {
         const int s = i % STAGES;
         mbar_wait_bounded(&full[s], (i / STAGES) & 1, &g_k11_flag, 17);
         tc_fence_after();
         const uint32_t base = smem_u32(stage + s * STAGE);
         const uint64_t a1 = umma_desc_sw128(base, 16, 1024), a2 = umma_desc_sw128(base + L_A_PLANE, 16, 1024);
-        const uint64_t w1 = umma_desc_sw128(base + 2 * L_A_PLANE, 16, 1024);
-        const uint64_t w2 = umma_desc_sw128(base + 2 * L_A_PLANE + W_PLANE, 16, 1024);
+        const uint64_t w12 = umma_desc_sw128(base + 2 * L_A_PLANE, 16, 1024);   // w1 rows, then w2 rows
 #pragma unroll
-        for (int ks = 0; ks < L_KC / 16; ++ks) {  // small terms first
-          mma_f16_ss(tmem_base, a2 + 2 * ks, w1 + 2 * ks, idesc, (i | ks) != 0);
-          mma_f16_ss(tmem_base, a1 + 2 * ks, w2 + 2 * ks, idesc, 1);
-          mma_f16_ss(tmem_base, a1 + 2 * ks, w1 + 2 * ks, idesc, 1);
+        for (int ks = 0; ks < L_KC / 16; ++ks) {
+          mma_f16_ss(tmem_base, a1 + 2 * ks, w12 + 2 * ks, idesc2, (i | ks) != 0);   // D1 += h1.w1, D2 += h1.w2
+          mma_f16_ss(tmem_base, a2 + 2 * ks, w12 + 2 * ks, idesc1, 1);               // D1 += h2.w1
         }
         tc_commit(&empty[s]);
       }
@@ -265,9 +268,12 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
     float* park = reinterpret_cast<float*>(stage);
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[2][16];
-      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0, v[0]);
-      tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0 + 16, v[1]);
+      uint32_t v[2][16], u[2][16];   // D1 (h1.w1 + h2.w1) and D2 (h1.w2) of the same 32 columns
+      const uint32_t tl = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + c0;
+      tmem_ld_x16(tl, v[0]);
+      tmem_ld_x16(tl + 16, v[1]);
+      tmem_ld_x16(tl + BN, u[0]);
+      tmem_ld_x16(tl + BN + 16, u[1]);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 2; ++g)
@@ -277,8 +283,10 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
           float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
           if (row_ok && n < a.N) {  // N % 4 == 0
             const float4 iw = __ldg(reinterpret_cast<const float4*>(a.inv_w + n));
-            o = make_float4(__uint_as_float(v[g][q]) * (ia * iw.x), __uint_as_float(v[g][q + 1]) * (ia * iw.y),
-                            __uint_as_float(v[g][q + 2]) * (ia * iw.z), __uint_as_float(v[g][q + 3]) * (ia * iw.w));
+            o = make_float4((__uint_as_float(v[g][q]) + __uint_as_float(u[g][q])) * (ia * iw.x),
+                            (__uint_as_float(v[g][q + 1]) + __uint_as_float(u[g][q + 1])) * (ia * iw.y),
+                            (__uint_as_float(v[g][q + 2]) + __uint_as_float(u[g][q + 2])) * (ia * iw.z),
+                            (__uint_as_float(v[g][q + 3]) + __uint_as_float(u[g][q + 3])) * (ia * iw.w));
             if (a.split_k == 1) finish(o, n);
           }
           if (a.split_k > 1) *reinterpret_cast<float4*>(park + (quarter * 32 + lane) * PITCH + cl) = o;
@@ -347,7 +355,7 @@ k11_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
