@@ -584,7 +584,7 @@ def x3_split(x2d: torch.Tensor) -> torch.Tensor:
 
 
 def x3_split_ln(x2d: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float) -> torch.Tensor:
-    '''fd_linear_x3_split_ln: operand buffer of LayerNorm(x2d) * gamma + beta (K % 128 == 0, K <= 2048).'''
+    '''fd_linear_x3_split_ln: operand buffer of LayerNorm(x2d) * gamma + beta (K % 64 == 0, K <= 8192).'''
     _need(x2d, 'x', torch.float32)
     _need(gamma, 'gamma', torch.float32)
     _need(beta, 'beta', torch.float32)
@@ -661,7 +661,7 @@ def linear_x3(x: Optional[torch.Tensor], weight: torch.Tensor, bias: Optional[to
 def attention_f32_supported(T: int, d: int) -> bool:
     '''Shapes K12 serves: K^T, V, the query rows and the probability strips of one head fit in shared memory.'''
     ni = 3 if T <= 96 else 9
-    floats = d * (T | 1) + T * d + 8 * d * 4 + 8 * 32 * ni * 4
+    floats = d * (32 * ni + 1) + T * d + 8 * d * 4 + 8 * 32 * ni * 4
     return T <= 288 and d % 4 == 0 and d <= 128 and floats * 4 <= 227 * 1024
 
 

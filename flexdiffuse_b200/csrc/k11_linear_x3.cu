@@ -11,13 +11,13 @@
 // accumulated in fp32 in TMEM, which carries the result to fp32 accuracy (error <= ~4e-7 |x| |w| per row
 // pair; tests/test_linear_x3_gpu.py).  Unlike K1P the scale is chosen PER ROW from the row's maximum
 // (max |x| 2^e in [2^13, 2^14)), so no activation range has to be assumed inside the towers.
-//   k11_split_rows_kernel   fp32 rows -> h1 / h2 planes + the row's inverse scale (weights once per
-//                           version, activations once per call; one warp per row)
+//   k11_split_kernel<V, LN> fp32 rows -> h1 / h2 planes + the row's inverse scale (weights once per version, activations
+//                           once per call; one 128-thread CTA per row, the row in registers); LN = true: the pre-LN
+//                           LayerNorm of the towers' blocks fused in front of the split
 //   k11_gemm_kernel<BN>     both operands by TMA (SWIZZLE_128B, K chunks of 64, multi-stage ring),
 //                           warps 0 / 2 producers, warp 1 MMA issuer (per k-step h1 x [w1; w2] as one M128 N=2BN MMA, then h2 x w1),
 //                           warps 2-5 epilogue: TMEM -> x inv_a[row] x inv_w[col] (+ bias, activation, residual) ->
 //                           fp32 global; with split-K the last CTA of a tile to finish adds the slices in ascending order
-//   k11_ln_split_kernel     LayerNorm fused with the split (the towers' pre-LN blocks feed every q|k|v and fc1 GEMM)
 #include <cuda_fp16.h>
 
 #include "fd_common.cuh"
@@ -37,105 +37,111 @@ __device__ __forceinline__ float act_apply(float v, int act) {
   return v;
 }
 
-// one warp per row: the row maximum picks the power of two, then the two-term split
-__global__ void __launch_bounds__(256) k11_split_rows_kernel(const float* __restrict__ x, __half* __restrict__ h1p,
-                                                             __half* __restrict__ h2p, float* __restrict__ inv_scale,
-                                                             int rows, int K) {
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * K);
-  const int k4 = K >> 2;
-  float mx = 0.f;
-  bool bad = false;
-  for (int c = lane; c < k4; c += 32) {
-    const float4 v = __ldg(xr + c);
-    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
-    bad |= !(fabsf(v.x) <= 3.0e38f) | !(fabsf(v.y) <= 3.0e38f) | !(fabsf(v.z) <= 3.0e38f) | !(fabsf(v.w) <= 3.0e38f);
-  }
+// Operand preparation: ONE CTA of 128 threads per row (a warp per row left 33 CTAs for the towers' 257 rows and
+// made K = 4096 a 14 us launch).  The row lives in registers (V float4 per thread, K = 512 V), the row maximum picks the
+// power of two, then the two-term split.  LN: y = (x - mean) rstd gamma + beta first, never written to memory.
+constexpr int SP_THREADS = 128;
+
+__device__ __forceinline__ float block_reduce_128(float v, bool is_max, float* red) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  bad = __any_sync(0xffffffffu, bad);
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = is_max ? fmaxf(v, u) : v + u;
+  }
+  const int w = threadIdx.x >> 5;
+  __syncthreads();   // red[] may still be read from the previous reduction
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  // fixed order over the 4 warps: bit-reproducible
+  return is_max ? fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) : (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+template <int V, bool LN>
+__global__ void __launch_bounds__(SP_THREADS) k11_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, float eps,
+                                                               __half* __restrict__ h1p, __half* __restrict__ h2p,
+                                                               float* __restrict__ inv_scale, int K) {
+  __shared__ float red[4];
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int k4 = K >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * K);
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tid + SP_THREADS * i;
+    v[i] = c < k4 ? __ldg(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  bool bad = false;
+  if (LN) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    const float mean = block_reduce_128(sum, false, red) / K;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i)
+      if (tid + SP_THREADS * i < k4) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        sq += (a * a + b * b) + (c * c + d * d);
+      }
+    sq = block_reduce_128(sq, false, red);
+    const float rstd = rsqrtf(sq / K + eps);
+    bad = !(sq <= 3.0e38f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = tid + SP_THREADS * i;
+      if (c < k4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        v[i].x = (v[i].x - mean) * rstd * g.x + bt.x;
+        v[i].y = (v[i].y - mean) * rstd * g.y + bt.y;
+        v[i].z = (v[i].z - mean) * rstd * g.z + bt.z;
+        v[i].w = (v[i].w - mean) * rstd * g.w + bt.w;
+      }
+    }
+  }
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
+    bad |= !(fabsf(v[i].x) <= 3.0e38f) | !(fabsf(v[i].y) <= 3.0e38f) | !(fabsf(v[i].z) <= 3.0e38f) | !(fabsf(v[i].w) <= 3.0e38f);
+  }
+  mx = block_reduce_128(mx, true, red);
   int ex = 0;
   if (mx > 0.f) frexpf(mx, &ex);            // mx = m 2^ex, m in [0.5, 1)
   ex = max(-100, min(100, ex));
   const float scale = exp2f(static_cast<float>(14 - ex));   // mx * scale in [2^13, 2^14)
-  if (bad && lane == 0) g_k11_flag = 1;
-  if (lane == 0) inv_scale[row] = exp2f(static_cast<float>(ex - 14));
+  if (bad) g_k11_flag = 1;
+  if (tid == 0) inv_scale[row] = exp2f(static_cast<float>(ex - 14));
   uint2* o1 = reinterpret_cast<uint2*>(h1p + static_cast<size_t>(row) * K);
   uint2* o2 = reinterpret_cast<uint2*>(h2p + static_cast<size_t>(row) * K);
-  for (int c = lane; c < k4; c += 32) {
-    const float4 v = __ldg(xr + c);
-    const float a = v.x * scale, b = v.y * scale, cc = v.z * scale, d = v.w * scale;
-    const __half2 p0 = __floats2half2_rn(a, b), p1 = __floats2half2_rn(cc, d);
-    const float2 f0 = __half22float2(p0), f1 = __half22float2(p1);
-    const __half2 q0 = __floats2half2_rn(a - f0.x, b - f0.y), q1 = __floats2half2_rn(cc - f1.x, d - f1.y);
-    o1[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
-    o2[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&q0), *reinterpret_cast<const uint32_t*>(&q1));
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = tid + SP_THREADS * i;
+    if (c < k4) {
+      const float a = v[i].x * scale, b = v[i].y * scale, cc = v[i].z * scale, d = v[i].w * scale;
+      const __half2 p0 = __floats2half2_rn(a, b), p1 = __floats2half2_rn(cc, d);
+      const float2 f0 = __half22float2(p0), f1 = __half22float2(p1);
+      const __half2 q0 = __floats2half2_rn(a - f0.x, b - f0.y), q1 = __floats2half2_rn(cc - f1.x, d - f1.y);
+      o1[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+      o2[c] = make_uint2(*reinterpret_cast<const uint32_t*>(&q0), *reinterpret_cast<const uint32_t*>(&q1));
+    }
   }
 }
 
-// LayerNorm fused with the operand split: y = (x - mean) rstd gamma + beta never leaves the registers of the warp that owns
-// the row; only the two fp16 planes and the inverse scale are written.  K = 128 V floats per row (V float4 per lane).
-template <int V>
-__global__ void __launch_bounds__(256) k11_ln_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                           const float* __restrict__ beta, float eps,
-                                                           __half* __restrict__ h1p, __half* __restrict__ h2p,
-                                                           float* __restrict__ inv_scale, int rows) {
-  constexpr int K = 128 * V;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + static_cast<size_t>(row) * K);
-  float4 v[V];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    v[i] = __ldg(xr + lane + 32 * i);
-    sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+template <bool LN>
+int launch_split(const float* x, const float* gamma, const float* beta, float eps, __half* h1, __half* h2, float* inv,
+                 int rows, int K, cudaStream_t st) {
+  const int v = (K / 4 + SP_THREADS - 1) / SP_THREADS;   // float4 per thread
+  switch (v) {
+#define FD_SP_CASE(V) case V: k11_split_kernel<V, LN><<<rows, SP_THREADS, 0, st>>>(x, gamma, beta, eps, h1, h2, inv, K); break;
+    FD_SP_CASE(1) FD_SP_CASE(2) FD_SP_CASE(3) FD_SP_CASE(4) FD_SP_CASE(5) FD_SP_CASE(6) FD_SP_CASE(7) FD_SP_CASE(8)
+    FD_SP_CASE(9) FD_SP_CASE(10) FD_SP_CASE(11) FD_SP_CASE(12) FD_SP_CASE(13) FD_SP_CASE(14) FD_SP_CASE(15) FD_SP_CASE(16)
+#undef FD_SP_CASE
+    default: return set_error(FD_ERR_ARG, "fd_linear_x3_split: K=%d exceeds 8192", K);
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum * (1.0f / K);
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    sq += (a * a + b * b) + (c * c + d * d);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-  const float rstd = rsqrtf(sq * (1.0f / K) + eps);
-  float mx = 0.f;
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * i);
-    v[i].x = (v[i].x - mean) * rstd * g.x + bt.x;
-    v[i].y = (v[i].y - mean) * rstd * g.y + bt.y;
-    v[i].z = (v[i].z - mean) * rstd * g.z + bt.z;
-    v[i].w = (v[i].w - mean) * rstd * g.w + bt.w;
-    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[i].x), fabsf(v[i].y)), fmaxf(fabsf(v[i].z), fabsf(v[i].w))));
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  int ex = 0;
-  if (mx > 0.f) frexpf(mx, &ex);
-  ex = max(-100, min(100, ex));
-  const float scale = exp2f(static_cast<float>(14 - ex));
-  if (lane == 0) {
-    inv_scale[row] = exp2f(static_cast<float>(ex - 14));
-    if (!(mx <= 3.0e38f) || !(sq <= 3.0e38f)) g_k11_flag = 1;
-  }
-  uint2* o1 = reinterpret_cast<uint2*>(h1p + static_cast<size_t>(row) * K);
-  uint2* o2 = reinterpret_cast<uint2*>(h2p + static_cast<size_t>(row) * K);
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    const float a = v[i].x * scale, b = v[i].y * scale, c = v[i].z * scale, d = v[i].w * scale;
-    const __half2 p0 = __floats2half2_rn(a, b), p1 = __floats2half2_rn(c, d);
-    const float2 f0 = __half22float2(p0), f1 = __half22float2(p1);
-    const __half2 q0 = __floats2half2_rn(a - f0.x, b - f0.y), q1 = __floats2half2_rn(c - f1.x, d - f1.y);
-    o1[lane + 32 * i] = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
-    o2[lane + 32 * i] = make_uint2(*reinterpret_cast<const uint32_t*>(&q0), *reinterpret_cast<const uint32_t*>(&q1));
-  }
+  FD_CUDA_OK(cudaGetLastError());
+  return FD_OK;
 }
 
 struct LArgs {
@@ -396,7 +402,8 @@ extern "C" int fd_linear_x3_split(const float* x_dev, int rows, int K, void* ope
                                   void* stream) {
   using namespace fd;
   FD_REQUIRE(x_dev && operand_dev, "fd_linear_x3_split: NULL pointer");
-  FD_REQUIRE(rows > 0 && K > 0 && K % L_KC == 0, "fd_linear_x3_split: need rows > 0 and K %% 64 == 0 (rows=%d, K=%d)", rows, K);
+  FD_REQUIRE(rows > 0 && K > 0 && K % L_KC == 0 && K <= 8192,
+             "fd_linear_x3_split: need rows > 0 and K a multiple of 64 up to 8192 (rows=%d, K=%d)", rows, K);
   FD_REQUIRE(operand_bytes >= fd_linear_x3_operand_bytes(rows, K), "fd_linear_x3_split: operand buffer too small");
   FD_REQUIRE(reinterpret_cast<uintptr_t>(x_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(operand_dev) % 256 == 0,
              "fd_linear_x3_split: x must be 16-byte and the operand buffer 256-byte aligned");
@@ -404,19 +411,16 @@ extern "C" int fd_linear_x3_split(const float* x_dev, int rows, int K, void* ope
   if (rc != FD_OK) return rc;
   const int64_t plane = (static_cast<int64_t>(rows) * K * 2 + 255) / 256 * 256;
   uint8_t* base = static_cast<uint8_t*>(operand_dev);
-  k11_split_rows_kernel<<<(rows + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x_dev, reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + plane),
-      reinterpret_cast<float*>(base + 2 * plane), rows, K);
-  FD_CUDA_OK(cudaGetLastError());
-  return FD_OK;
+  return launch_split<false>(x_dev, nullptr, nullptr, 0.f, reinterpret_cast<__half*>(base), reinterpret_cast<__half*>(base + plane),
+                             reinterpret_cast<float*>(base + 2 * plane), rows, K, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fd_linear_x3_split_ln(const float* x_dev, int rows, int K, const float* gamma_dev, const float* beta_dev,
                                      float eps, void* operand_dev, int64_t operand_bytes, void* stream) {
   using namespace fd;
   FD_REQUIRE(x_dev && gamma_dev && beta_dev && operand_dev, "fd_linear_x3_split_ln: NULL pointer");
-  FD_REQUIRE(rows > 0 && K > 0 && K % 128 == 0 && K <= 2048,
-             "fd_linear_x3_split_ln: need rows > 0 and K a multiple of 128 up to 2048 (rows=%d, K=%d)", rows, K);
+  FD_REQUIRE(rows > 0 && K > 0 && K % L_KC == 0 && K <= 8192,
+             "fd_linear_x3_split_ln: need rows > 0 and K a multiple of 64 up to 8192 (rows=%d, K=%d)", rows, K);
   FD_REQUIRE(operand_bytes >= fd_linear_x3_operand_bytes(rows, K), "fd_linear_x3_split_ln: operand buffer too small");
   FD_REQUIRE(reinterpret_cast<uintptr_t>(x_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(gamma_dev) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(beta_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(operand_dev) % 256 == 0,
@@ -428,16 +432,7 @@ extern "C" int fd_linear_x3_split_ln(const float* x_dev, int rows, int K, const 
   __half* h1 = reinterpret_cast<__half*>(base);
   __half* h2 = reinterpret_cast<__half*>(base + plane);
   float* inv = reinterpret_cast<float*>(base + 2 * plane);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (rows + 7) / 8;
-  switch (K / 128) {
-#define FD_LN_CASE(V) case V: k11_ln_split_kernel<V><<<grid, 256, 0, st>>>(x_dev, gamma_dev, beta_dev, eps, h1, h2, inv, rows); break;
-    FD_LN_CASE(1) FD_LN_CASE(2) FD_LN_CASE(3) FD_LN_CASE(4) FD_LN_CASE(5) FD_LN_CASE(6) FD_LN_CASE(7) FD_LN_CASE(8)
-    FD_LN_CASE(9) FD_LN_CASE(10) FD_LN_CASE(11) FD_LN_CASE(12) FD_LN_CASE(13) FD_LN_CASE(14) FD_LN_CASE(15) FD_LN_CASE(16)
-#undef FD_LN_CASE
-  }
-  FD_CUDA_OK(cudaGetLastError());
-  return FD_OK;
+  return launch_split<true>(x_dev, gamma_dev, beta_dev, eps, h1, h2, inv, rows, K, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int fd_linear_x3(const void* act_operand_dev, int M, const void* weight_operand_dev, int N, int K,

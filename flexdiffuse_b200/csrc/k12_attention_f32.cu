@@ -27,12 +27,12 @@ struct AtArgs {
   float scale;
 };
 
-// NI = ceil(T / 32) keys per lane
-template <int NI>
+// NI = keys per lane (32 NI >= T), NM = output columns per lane (32 NM >= d), DFULL: d == 32 NM (no column guards)
+template <int NI, int NM, bool DFULL>
 __global__ void __launch_bounds__(AT_THREADS, 1) k12_attn_f32_kernel(const AtArgs a) {
   extern __shared__ float at_smem[];
   const int T = a.T, d = a.d;
-  const int Tp = T | 1;                       // odd pitch: conflict-free transposed stores
+  constexpr int Tp = 32 * NI + 1;             // odd pitch (conflict-free transposed stores) covering every lane's keys
   float* Kt = at_smem;                        // [d][Tp]
   float* Vs = Kt + static_cast<size_t>(d) * Tp;          // [T][d]
   float* Qs = Vs + static_cast<size_t>(T) * d;           // [AT_WARPS][d][AT_ROWS]
@@ -75,6 +75,12 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k12_attn_f32_kernel(const AtArg
       }
     }
   }
+  // keys [t_keys, 32 NI) do not exist (or are masked for every query of this CTA): zero columns, so the score loop
+  // runs without guards (their scores are dropped by the softmax mask)
+  for (int idx = tid; idx < d * (32 * NI - t_keys); idx += AT_THREADS) {
+    const int dd = idx / (32 * NI - t_keys), j = t_keys + idx - dd * (32 * NI - t_keys);
+    Kt[dd * Tp + j] = 0.f;
+  }
   // this warp's 4 query rows, interleaved [dd][row] so one float4 load serves the 4 rows
   float* qw = Qs + warp * d * AT_ROWS;
   const int row0 = q0 + warp * AT_ROWS;
@@ -98,7 +104,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k12_attn_f32_kernel(const AtArg
     const float* kr = Kt + dd * Tp + lane;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
-      const float kv = (lane + 32 * i < t_keys) ? kr[32 * i] : 0.f;
+      const float kv = kr[32 * i];
       s[0][i] = fmaf(qv.x, kv, s[0][i]);
       s[1][i] = fmaf(qv.y, kv, s[1][i]);
       s[2][i] = fmaf(qv.z, kv, s[2][i]);
@@ -132,19 +138,19 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k12_attn_f32_kernel(const AtArg
   }
   __syncwarp();
   // ---- out[r][lane + 32 m] = sum_j p[r][j] v[j][lane + 32 m]   (d <= 128: up to 4 columns per lane)
-  float o[AT_ROWS][4];
+  float o[AT_ROWS][NM];
 #pragma unroll
   for (int r = 0; r < AT_ROWS; ++r)
 #pragma unroll
-    for (int m = 0; m < 4; ++m) o[r][m] = 0.f;
-  const int nm = (d + 31) >> 5;
+    for (int m = 0; m < NM; ++m) o[r][m] = 0.f;
   const int jmax = a.causal ? min(T, row0 + AT_ROWS) : T;
+#pragma unroll 2
   for (int j = 0; j < jmax; ++j) {
     const float4 pv = *reinterpret_cast<const float4*>(pw + j * AT_ROWS);
     const float* vr = Vs + static_cast<size_t>(j) * d + lane;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      if (m < nm && lane + 32 * m < d) {
+    for (int m = 0; m < NM; ++m) {
+      if (DFULL || lane + 32 * m < d) {
         const float vv = vr[32 * m];
         o[0][m] = fmaf(pv.x, vv, o[0][m]);
         o[1][m] = fmaf(pv.y, vv, o[1][m]);
@@ -159,8 +165,8 @@ __global__ void __launch_bounds__(AT_THREADS, 1) k12_attn_f32_kernel(const AtArg
     if (t < T) {
       float* orow = a.out + (static_cast<size_t>(b) * T + t) * (static_cast<size_t>(a.H) * d) + h * d;
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-        if (m < nm && lane + 32 * m < d) orow[lane + 32 * m] = o[r][m];
+      for (int m = 0; m < NM; ++m)
+        if (DFULL || lane + 32 * m < d) orow[lane + 32 * m] = o[r][m];
     }
   }
 }
@@ -183,10 +189,10 @@ extern "C" int fd_attention_f32(const float* q_dev, const float* k_dev, const fl
   FD_REQUIRE(static_cast<int64_t>(B) * H <= 65535, "fd_attention_f32: too many (batch, head) pairs");
   int rc = check_device();
   if (rc != FD_OK) return rc;
-  const int NI = (T + 31) / 32;
-  const int Tp = T | 1;
+  const int ni = T <= 96 ? 3 : 9;
+  const int Tp = 32 * ni + 1;
   const size_t smem = (static_cast<size_t>(d) * Tp + static_cast<size_t>(T) * d + AT_WARPS * d * AT_ROWS +
-                       static_cast<size_t>(AT_WARPS) * 32 * (NI <= 3 ? 3 : 9) * AT_ROWS) * sizeof(float);
+                       static_cast<size_t>(AT_WARPS) * 32 * ni * AT_ROWS) * sizeof(float);
   FD_REQUIRE(smem <= 227 * 1024, "fd_attention_f32: T=%d, d=%d need %zu bytes of shared memory", T, d, smem);
   AtArgs a;
   a.q = q_dev;
@@ -202,13 +208,25 @@ extern "C" int fd_attention_f32(const float* q_dev, const float* k_dev, const fl
   a.scale = scale;
   dim3 grid((T + AT_QB - 1) / AT_QB, B * H);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (NI <= 3) {
-    FD_CUDA_OK(cudaFuncSetAttribute(k12_attn_f32_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k12_attn_f32_kernel<3><<<grid, AT_THREADS, smem, st>>>(a);
-  } else {
-    FD_CUDA_OK(cudaFuncSetAttribute(k12_attn_f32_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k12_attn_f32_kernel<9><<<grid, AT_THREADS, smem, st>>>(a);
-  }
+  const int nm = (d + 31) / 32;
+  const bool dfull = d % 32 == 0;
+#define FD_AT_LAUNCH(NI_, NM_, DF_)                                                                                         \
+  do {                                                                                                                      \
+    FD_CUDA_OK(cudaFuncSetAttribute(k12_attn_f32_kernel<NI_, NM_, DF_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                    static_cast<int>(smem)));                                                               \
+    k12_attn_f32_kernel<NI_, NM_, DF_><<<grid, AT_THREADS, smem, st>>>(a);                                                  \
+  } while (0)
+#define FD_AT_NM(NI_)                                                          \
+  do {                                                                         \
+    if (nm == 1) { if (dfull) FD_AT_LAUNCH(NI_, 1, true); else FD_AT_LAUNCH(NI_, 1, false); }      \
+    else if (nm == 2) { if (dfull) FD_AT_LAUNCH(NI_, 2, true); else FD_AT_LAUNCH(NI_, 2, false); } \
+    else if (nm == 3) { if (dfull) FD_AT_LAUNCH(NI_, 3, true); else FD_AT_LAUNCH(NI_, 3, false); } \
+    else { if (dfull) FD_AT_LAUNCH(NI_, 4, true); else FD_AT_LAUNCH(NI_, 4, false); }              \
+  } while (0)
+  if (ni == 3) FD_AT_NM(3);
+  else FD_AT_NM(9);
+#undef FD_AT_NM
+#undef FD_AT_LAUNCH
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

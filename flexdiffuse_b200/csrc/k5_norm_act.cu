@@ -539,6 +539,11 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
       // do not split a strip below 4 KB per CTA just to fill the SMs: a wider cluster barrier costs more
       while (cl < 8 && (set_bytes / cl > 64 * 1024 || (n_sets * cl < sm_count() && set_bytes / cl > gn_min_cta_bytes))) cl *= 2;
       while (cl > 1 && HW < cl * 8) cl /= 2;
+      static const int force_cl = [] {  // development override (A/B of the cluster width)
+        const char* e = getenv("FD_GN_FORCE_CL");
+        return e ? atoi(e) : 0;
+      }();
+      if (force_cl > 0 && set_bytes / force_cl <= 96 * 1024 && HW >= force_cl * 8) cl = force_cl;
       const int rows_per_cta = (HW + cl - 1) / cl;
       const int64_t smem = static_cast<int64_t>(rows_per_cta) * sv * 16;
       // > 96 KB per CTA (C=960 at 64x64: 123 KB) measured 2.4x slower than the streaming path

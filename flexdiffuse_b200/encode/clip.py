@@ -122,7 +122,7 @@ def _x3_encoder(encoder, hidden: torch.Tensor, causal: bool) -> torch.Tensor:
     M = B * T
 
     def ln_operand(ln, x):   # operand buffer of ln(x): fused LayerNorm + split where K11 has the kernel
-        if C % 128 == 0 and C <= 2048 and ln.elementwise_affine and ln.bias is not None:
+        if C % 64 == 0 and C <= 8192 and ln.elementwise_affine and ln.bias is not None:
             return _native.x3_split_ln(x, ln.weight, ln.bias, ln.eps)
         return _native.x3_split(ln(x))
 

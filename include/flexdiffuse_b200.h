@@ -219,12 +219,12 @@ int fd_visual_projection_range_flag(void);
 #define FD_LINEAR_ACT_QUICK_GELU 1   /* x * sigmoid(1.702 x): CLIP's hidden_act               */
 #define FD_LINEAR_ACT_GELU       2   /* erf GELU                                              */
 int64_t fd_linear_x3_operand_bytes(int rows, int K);
-int fd_linear_x3_split(const float* x_dev,      /* [rows, K] fp32 row-major, K % 64 == 0        */
+int fd_linear_x3_split(const float* x_dev,      /* [rows, K] fp32 row-major, K % 64 == 0, <= 8192 */
                        int rows, int K,
                        void* operand_dev,       /* >= fd_linear_x3_operand_bytes, 256-B aligned  */
                        int64_t operand_bytes, void* stream);
 /* LayerNorm fused with the split: operand of y = LayerNorm(x) * gamma + beta (y itself is never written). */
-int fd_linear_x3_split_ln(const float* x_dev, int rows, int K,   /* K % 128 == 0, K <= 2048             */
+int fd_linear_x3_split_ln(const float* x_dev, int rows, int K,   /* K % 64 == 0, K <= 8192              */
                           const float* gamma_dev, const float* beta_dev, float eps,
                           void* operand_dev, int64_t operand_bytes, void* stream);
 int fd_linear_x3(const void* act_operand_dev,   /* split [M, K]                                  */

@@ -88,6 +88,13 @@ def main(mode: str):
     dec = torch.randn(1, 3, 512, 512, device=dev, generator=g).bfloat16().contiguous(
         memory_format=torch.channels_last)
 
+    tx = torch.randn(257, 1024, device=dev, generator=g)
+    tg, tb = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+    w_qkv, b_qkv = torch.randn(3072, 1024, device=dev, generator=g) * 0.03, torch.zeros(3072, device=dev)
+    w_o, b_o = torch.randn(1024, 1024, device=dev, generator=g) * 0.03, torch.zeros(1024, device=dev)
+    w_fc1, b_fc1 = torch.randn(4096, 1024, device=dev, generator=g) * 0.03, torch.zeros(4096, device=dev)
+    w_fc2 = torch.randn(1024, 4096, device=dev, generator=g) * 0.03
+
     def run():
         for m, q in zip(picks, qs):
             _native.cross_attn(q, kv.kv, m.k_col_off, m.v_col_off, idx, m.heads, 77, 80,
@@ -101,6 +108,14 @@ def main(mode: str):
         unet.build_kv_cache(ctx9)
         _native.sim_blend(txt, img, [prm], lin)
         _native.image_tail_u8(dec)
+        # K11 / K12 at the ViT-L/14 shapes (M = 257): LN-fused split, q|k|v GEMM, attention core, out_proj (split-K
+        # cluster + residual), fc1 + quick_gelu, plain split, fc2 (split-K 4)
+        op = _native.x3_split_ln(tx, tg, tb, 1e-5)
+        qkv = _native.linear_x3(None, w_qkv, b_qkv, operand=op, rows=257).view(1, 257, 3072)
+        o = _native.attention_f32(qkv[..., :1024], qkv[..., 1024:2048], qkv[..., 2048:], 16, 0.125, False)
+        h1 = _native.linear_x3(o.view(257, 1024), w_o, b_o, residual=tx)
+        h2 = _native.linear_x3(h1, w_fc1, b_fc1, act=_native.LINEAR_ACT_QUICK_GELU)
+        _native.linear_x3(h2, w_fc2, b_o, residual=h1)
 
     run()
     torch.cuda.synchronize()
