@@ -34,7 +34,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
                'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3_split_ln', 'fd_linear_x3',
                'fd_linear_x3_flag',
-               'fd_attention_f32')
+               'fd_attention_f32', 'fd_ff_geglu')
 
 
 class NativeError(RuntimeError):
@@ -154,6 +154,8 @@ def lib() -> C.CDLL:
     l.fd_attention_f32.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_int, vp]
     l.fd_attention_f32.restype = C.c_int
+    l.fd_ff_geglu.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    l.fd_ff_geglu.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -680,3 +682,28 @@ def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
                                  float(scale), int(causal), stream_ptr(q.device)), 'fd_attention_f32')
     count_launch()
     return out
+
+
+# --------------------------------------------------------------------------- K13
+def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    '''fd_ff_geglu: x [..., K] bf16, weight [2F, K] bf16 (value rows, gate rows), bias [2F] bf16 ->
+    (x W_v^T + b_v) * gelu(x W_g^T + b_g) as [..., F] bf16; the [.., 2F] projection is never materialised.'''
+    _need(weight, 'weight', torch.bfloat16)
+    _need(bias, 'bias', torch.bfloat16)
+    if not x.is_cuda or x.dtype != torch.bfloat16:
+        raise NativeError('ff_geglu needs CUDA bfloat16 input')
+    x2 = x.reshape(-1, x.shape[-1])
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    M, K = x2.shape
+    F2 = weight.shape[0]
+    if weight.shape[1] != K or F2 % 2 or bias.numel() != F2:
+        raise NativeError(f'ff_geglu: weight {tuple(weight.shape)} / bias {tuple(bias.shape)} do not fit K={K}')
+    out = torch.empty((M, F2 // 2), dtype=torch.bfloat16, device=x.device)
+    check(lib().fd_ff_geglu(ptr(x2), ptr(weight), ptr(bias), ptr(out), M, F2 // 2, K, stream_ptr(x.device)), 'fd_ff_geglu')
+    count_launch()
+    return out.reshape(*x.shape[:-1], F2 // 2)
+
+
+def ff_geglu_supported(K: int, F: int) -> bool:
+    return K % 64 == 0 and F % 128 == 0

@@ -208,13 +208,21 @@ class CrossAttention(nn.Module):
         return self.to_out[0](o)
 
 
+FF_GEGLU_FUSED = True   # K13 on / off (off = cuBLAS projection + K6); profiles/time_unet.py A/Bs the two
+
+
 class GEGLU(nn.Module):
     def __init__(self, dim: int, inner: int):
         super().__init__()
         self.proj = nn.Linear(dim, inner * 2)
 
     def forward(self, x):
-        return _native.geglu(self.proj(x))  # K6: x * gelu(gate) in one pass
+        w = self.proj.weight
+        if (FF_GEGLU_FUSED and x.is_cuda and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+                and self.proj.bias is not None and _native.ff_geglu_supported(w.shape[1], w.shape[0] // 2)):
+            # K13: the projection GEMM with value * gelu(gate) in its epilogue (the [M, 8 C] tensor is never written)
+            return _native.ff_geglu(x, w, self.proj.bias)
+        return _native.geglu(self.proj(x))  # cuBLAS + K6: x * gelu(gate) in one pass
 
 
 class FeedForward(nn.Module):

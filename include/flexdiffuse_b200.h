@@ -255,6 +255,18 @@ int fd_attention_f32(const float* q_dev, const float* k_dev, const float* v_dev,
                      int H, int d,                  /* d % 4 == 0, d <= 128                       */
                      float scale, int causal, void* stream);
 
+/* ---- K13: feed-forward GEGLU projection with the activation in the GEMM epilogue -------- *
+ * Replaces `GEGLU.proj` (nn.Linear(C, 8C)) + `hidden * F.gelu(gate)` of diffusers' FeedForward in every
+ * BasicTransformerBlock of the UNet call at pipeline/guide.py:56-58:
+ *     out[m, f] = (x[m,:] . w[f,:] + b[f]) * gelu(x[m,:] . w[F + f,:] + b[F + f])
+ * tcgen05 cta_group::2 GEMM; the [M, 2F] projection never reaches memory.                       */
+int fd_ff_geglu(const void* x_bf16_dev,     /* [M, K] bf16 row-major tokens                     */
+                const void* w_bf16_dev,     /* [2F, K] bf16: value rows, then gate rows           */
+                const void* bias_bf16_dev,  /* [2F] bf16                                          */
+                void*       out_bf16_dev,   /* [M, F] bf16                                        */
+                int M, int F, int K,        /* F % 128 == 0, K % 64 == 0                          */
+                void* stream);
+
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
  * Replaces the 32 bias-free `to_k(context)` / `to_v(context)` Linears that diffusers'
  * CrossAttention.forward recomputes for each of the 16 attn2 layers at every step,

@@ -35,12 +35,13 @@ def main(mode: str):
     unet = factory.build_unet(dev, torch.bfloat16, seed=0)
     g = torch.Generator(device=dev).manual_seed(0)
     uncond = torch.randn(1, 77, 768, device=dev, generator=g)
-    embeds = torch.randn(1, 77, 768, device=dev, generator=g)
+    B = int(os.environ.get('FD_PROF_BATCH', '1'))   # images per step (FD_PROF_BATCH=8: the batched regime of configs[2..4])
+    embeds = torch.randn(B, 77, 768, device=dev, generator=g)
     if mode == 'step':
         guide = SimpleGuide(Enc(uncond), unet, 7.5, 50, embeds, use_cuda_graph=False)
         sched = schedulers.DDIMScheduler()
         sched.set_timesteps(50)
-        x = torch.randn(1, 4, 64, 64, device=dev, generator=g)
+        x = torch.randn(B, 4, 64, 64, device=dev, generator=g)
         buf = guide.model_input_buffer(x)
         buf.copy_(x)
         ts = [int(t) for t in sched.timesteps]
