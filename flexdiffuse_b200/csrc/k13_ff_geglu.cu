@@ -177,18 +177,17 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
       // the accumulator is in registers: hand the TMEM buffer back before the arithmetic
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // on the LEADER's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // on the LEADER's barrier
       uint8_t* buf = my_stage + (local & 1) * G_OUT_CHUNK;
       if (issuer) tma_store_wait_read<1>();
       named_bar_sync(1 + half, 128);   // staging buffer free, this tile's biases visible
-      const float4* bv4 = reinterpret_cast<const float4*>(bs);   // 64 value biases, then 64 gate biases (fp32)
-      const float4* bg4 = bv4 + 16;
+      const uint32_t bv4 = smem_u32(bs), bg4 = bv4 + 256;   // 64 value biases, then 64 gate biases (fp32)
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float4 bva = bv4[4 * g + 2 * h], bvb = bv4[4 * g + 2 * h + 1];
-          const float4 bga = bg4[4 * g + 2 * h], bgb = bg4[4 * g + 2 * h + 1];
+          const float4 bva = lds_f4(bv4 + 16 * (4 * g + 2 * h)), bvb = lds_f4(bv4 + 16 * (4 * g + 2 * h + 1));
+          const float4 bga = lds_f4(bg4 + 16 * (4 * g + 2 * h)), bgb = lds_f4(bg4 + 16 * (4 * g + 2 * h + 1));
           const float bvv[8] = {bva.x, bva.y, bva.z, bva.w, bvb.x, bvb.y, bvb.z, bvb.w};
           const float bgg[8] = {bga.x, bga.y, bga.z, bga.w, bgb.x, bgb.y, bgb.z, bgb.w};
           uint32_t pk[4];

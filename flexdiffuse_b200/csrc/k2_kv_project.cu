@@ -338,7 +338,7 @@ k2_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // on the LEADER's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tmem_empty[acc]), 0));  // on the LEADER's barrier
     }
     if (issuer) tma_store_wait_all();
   }
