@@ -367,6 +367,31 @@ def kernel_rooflines(dev, unet, peaks):
                      traffic_captured_at=NCU_CAPTURED_AT,
                      kernel='k2_gemm_kernel (M=720,N=24960,K=768; 9 contexts)',
                      avg_launch_us=t * 1e6, cublas_same_shape_us=t_cublas * 1e6, peak_of=peaks['source'])
+    # ---- K13: the GEGLU projections of all 16 feed-forward blocks of one UNet forward at 32 samples (batch 16, CFG), tensor
+    # bound: one launch per site replacing cuBLAS nn.Linear(C, 8C) + K6; algorithmic flops = 2 M C 8C
+    sites13 = []
+    for blk in (m for m in unet.modules() if m.__class__.__name__ == 'GEGLU'):
+        C = blk.proj.weight.shape[1]
+        sites13.append((torch.randn(32 * site_nq[C], C, device=dev).bfloat16(), blk.proj.weight, blk.proj.bias))
+    sites13[6] = (sites13[6][0][:32 * 64].contiguous(),) + sites13[6][1:]  # mid block: 8x8 latent
+    fl13 = sum(2.0 * x.shape[0] * x.shape[1] * w.shape[0] for x, w, _ in sites13)
+    by13 = sum(2.0 * (x.numel() + w.numel() + x.shape[0] * w.shape[0] // 2) for x, w, _ in sites13)
+    import torch.nn.functional as F13
+    t13 = _time_cuda(_graphed(lambda: [_native.ff_geglu(x, w, b) for x, w, b in sites13]).replay, 5)
+    t13_old = _time_cuda(_graphed(lambda: [_native.geglu(F13.linear(x, w, b)) for x, w, b in sites13]).replay, 5)
+    t13_gemm = _time_cuda(_graphed(lambda: [F13.linear(x, w, b) for x, w, b in sites13]).replay, 5)
+    out['k13'] = dict(bound='tensor', achieved=fl13 / t13 / 1e12, peak=peaks['tensor'], unit='TFLOP/s',
+                      frac=fl13 / t13 / 1e12 / peaks['tensor'],
+                      frac_of_sustained=(fl13 / t13 / 1e12 / peaks['tensor_sustained']
+                                         if peaks.get('tensor_sustained') else None),
+                      traffic=NCU_TRAFFIC_BYTES.get('k13'), traffic_captured_at=NCU_CAPTURED_AT,
+                      algorithmic_flops_per_launch=fl13 / len(sites13), algorithmic_bytes_per_launch=by13 / len(sites13),
+                      kernel='k13_ff_geglu_kernel (fd_ff_geglu: the 16 GEGLU projections of one UNet forward, 32 samples; '
+                             'cta_group::2 tcgen05 GEMM with value * gelu(gate) in the epilogue)',
+                      launches=len(sites13), avg_launch_us=t13 / len(sites13) * 1e6, fused_us=t13 * 1e6,
+                      same_work_cublas_k6_us=t13_old * 1e6, cublas_gemm_alone_us=t13_gemm * 1e6,
+                      peak_of=peaks['source'])
+    del sites13
     # ---- K1: blends/s -- 1024 prompts x 1 shared guide image, the reference's default parameters
     # (Linear (0, 0.5) + Clustered 0.5 + Threshold (0.5, 0.5): BASELINE.json configs[0]) on planted
     # inputs that do not hit the adjacent-peak ZeroDivisionError
@@ -958,6 +983,7 @@ def main():
         line['roofline_k2'] = kr['k2']
         line['roofline_k1'] = kr['k1']
         line['roofline_k5'] = kr['k5']
+        line['roofline_k13'] = kr['k13']
     if rank == 0 and world == 1 and extras:
         # the other single-GPU BASELINE configs, the torch GPU baseline and the CPU baselines: N = 1 only
         line['other_configs'] = {'config2': run_config2(dev, pipe_factory, unet),

@@ -351,7 +351,183 @@ k2_gemm2_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant_
   }
 }
 
-int g_k2_variant = 2;  // development aid: 2 = cta_group::2 pairs when M > 128, 1 = v3 (cta_group::1)
+// v5: clusters of SIX CTAs = three cta_group::2 pairs that work on the same 256-column weight tile and three adjacent
+// 256-row context blocks (M = 720: the whole context).  v4 at N = 256 x M = 256 per pair pulls 223 MB through L2 for
+// the 9-context shape (every weight tile three times, the context once per weight tile), which at the ~6300 B / clk
+// the L2 slices deliver chip-wide (B300_MICROARCH "LTS cap"; K13's large shapes sit exactly on it) is 18 us of its 25.
+// Here each CTA loads a THIRD of its pair-half of the weight tile (48 / 40 / 40 rows) and TMA-multicasts it to the same-rank
+// CTAs of all three pairs, so a weight byte leaves L2 once: 153 MB.  A stage is refilled only when all three pairs have
+// consumed it (every pair leader's tcgen05.commit is multicast to the six empty barriers, count 3).  The multicast's
+// complete_tx lands on the barrier at the same offset in the destination CTA's PAIR LEADER (.cta_group::2 form, peer bit of the
+// barrier address cleared).  Only 22 such clusters fit on the 148 SMs (132 SMs, profiles/microbench/cluster_occupancy.cu).
+// MEASURED (profiles/k2_bench.py, warm L2): correct at the first run, 26.4 us vs v4 23.6 us at M = 720 (47.5 vs 43.8 at M = 1360):
+// a tile runs 10 % faster (5.3 vs 5.9 us) but 98 tiles on 22 clusters are 5 waves instead of 4 -- the bytes each SM takes in
+// per k-block (32 KB, ~35-44 B / clk achieved) are unchanged by multicast, and that, not the L2 read count, is the bound.
+// Kept as an opt-in variant (fd_debug_set_k2_variant(3)) for the comparison; v4 stays the product path.
+constexpr int K2_PAIRS3 = 3;
+constexpr int K2_CLUSTER3 = 2 * K2_PAIRS3;
+__device__ __forceinline__ void tma_load_2d_2cta_mcast(void* dst, const CUtensorMap* map, uint32_t bar_addr, int c0, int c1,
+                                                       uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_addr), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(K2_THREADS2, 1)
+k2_gemm3_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b48,
+                const __grid_constant__ CUtensorMap tm_b40, const __grid_constant__ CUtensorMap tm_out, int K, int m_groups,
+                int n_tiles) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* out_stage = smem + STAGES2 * STAGE2_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(out_stage + OUT_BUFS2 * OUT_CHUNK_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full = empty_bar + STAGES2;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2] (the pair leader's copy counts: 2 x 8 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = K / BK;
+  const int total_tiles = m_groups * n_tiles;
+  const uint32_t crank = cluster_cta_rank();       // 0..5
+  const uint32_t q = crank >> 1, r = crank & 1;    // pair within the cluster, rank within the pair
+  const bool leader = r == 0;
+  const int first_tile = static_cast<int>(blockIdx.x / K2_CLUSTER3);
+  const int tile_stride = static_cast<int>(gridDim.x / K2_CLUSTER3);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_b48);
+    tma_prefetch_desc(&tm_b40);
+    tma_prefetch_desc(&tm_out);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], K2_PAIRS3);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 16);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();  // all six CTAs' barriers and TMEM exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // this CTA's third of the pair-half of the weight tile: rows [b_off, b_off + b_rows) of the 128
+      const int b_off = q == 0 ? 0 : (q == 1 ? 48 : 88);
+      const CUtensorMap* tm_b = q == 0 ? &tm_b48 : &tm_b40;
+      const uint16_t mask = static_cast<uint16_t>(0x15u << r);  // the same-rank CTAs of the three pairs
+      int it = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
+        const int m_blk = (tile % m_groups) * K2_PAIRS3 + static_cast<int>(q), n_blk = tile / m_groups;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait_bounded(&empty_bar[s], ((it / STAGES2) & 1) ^ 1, &g_k2_flag, 11);  // all three pairs consumed it
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * STAGE2_BYTES);
+          const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[s]), 2 * q);
+          tma_load_2d_2cta(smem + s * STAGE2_BYTES, &tm_a, lead_bar, kb * BK, m_blk * 2 * BM + static_cast<int>(r) * BM);
+          tma_load_2d_2cta_mcast(smem + s * STAGE2_BYTES + A_STAGE_BYTES + b_off * 128, tm_b,
+                                 smem_u32(&full_bar[s]) & 0xFEFFFFFFu, kb * BK,
+                                 n_blk * BN + static_cast<int>(r) * (BN / 2) + b_off, mask);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && elect_one()) {
+      constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 2 * BM, BN, 0, 0);
+      const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * q));
+      int it = 0, local = 0;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+        const int acc = local & 1;
+        mbar_wait_bounded(&tmem_empty[acc], ((local >> 1) & 1) ^ 1, &g_k2_flag, 12);  // both epilogues drained it
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % STAGES2;
+          mbar_wait_bounded(&full_bar[s], (it / STAGES2) & 1, &g_k2_flag, 13);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(smem_u32(smem + s * STAGE2_BYTES), 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(smem_u32(smem + s * STAGE2_BYTES + A_STAGE_BYTES), 16, 1024);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            mma_f16_ss_2cta(d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          tc_commit_2cta_mcast(&empty_bar[s], 0x3F);  // one of the three arrivals every CTA of the cluster waits for
+        }
+        tc_commit_2cta_mcast(&tmem_full[acc], pair_mask);  // both epilogues of this pair may read their half
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int row = quarter * 32 + lane;
+    const bool issuer = (threadIdx.x - 64) % 128 == 0;  // first thread of each half
+    uint8_t* my_stage = out_stage + half * 2 * OUT_CHUNK_BYTES;
+    int local = 0, chunk_no = 0;
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+      const int m_blk = (tile % m_groups) * K2_PAIRS3 + static_cast<int>(q), n_blk = tile / m_groups;
+      const int acc = local & 1;
+      mbar_wait_bounded(&tmem_full[acc], (local >> 1) & 1, &g_k2_flag, 14);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + acc * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 64, ++chunk_no) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) tmem_ld_x16(tbase + c0 + 16 * g, v[g]);
+        tmem_ld_wait();
+        uint8_t* buf = my_stage + (chunk_no & 1) * OUT_CHUNK_BYTES;
+        if (issuer) tma_store_wait_read<1>();
+        named_bar_sync(1 + half, 128);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 b = __floats2bfloat162_rn(__uint_as_float(v[g][8 * h + 2 * j]),
+                                                       __uint_as_float(v[g][8 * h + 2 * j + 1]));
+              pk[j] = *reinterpret_cast<uint32_t*>(&b);
+            }
+            *reinterpret_cast<uint4*>(buf + sw128_offset(row, 2 * g + h)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + half, 128);
+        if (issuer) {
+          tma_store_2d(&tm_out, buf, n_blk * BN + c0, m_blk * 2 * BM + static_cast<int>(r) * BM);
+          tma_store_commit();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster_relaxed(mapa_rank(smem_u32(&tmem_empty[acc]), 2 * q));  // the pair LEADER's barrier
+    }
+    if (issuer) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_barrier();  // no CTA exits (or frees TMEM) while a CTA of the cluster may still signal / write / multiply into it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+}
+
+int g_k2_variant = 2;  // 2 = v4 cta_group::2 pairs when M > 128 (default), 1 = v3, 3 = v5 six-CTA clusters when M > 512 (measured slower)
 
 }  // namespace
 }  // namespace fd
@@ -419,7 +595,44 @@ extern "C" int fd_kv_project(const void* ctx_bf16_dev, const void* w_bf16_dev, v
   const int m_tiles = (M + BM - 1) / BM, n_tiles = (N + BN - 1) / BN;
   const int total = m_tiles * n_tiles;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (g_k2_variant == 2 && m_tiles >= 2 && sms >= 2) {
+  if (g_k2_variant == 3 && m_tiles >= 5) {
+    // v5: six-CTA clusters, three pairs x 256 rows; m groups of 768 rows (OOB rows: TMA zero-fills and clips)
+    CUtensorMap tm_b48, tm_b40;
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box48[2] = {BK, 48}, box40[2] = {BK, 40};
+    rc = encode_tmap(&tm_b48, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_bf16_dev, dims, strides, box48, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+    rc = encode_tmap(&tm_b40, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_bf16_dev, dims, strides, box40, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != FD_OK) return rc;
+    static thread_local int attr3_device = -1;
+    static thread_local int max_clusters = 0;
+    const int m_groups = (m_tiles + 2 * K2_PAIRS3 - 1) / (2 * K2_PAIRS3);
+    const int tiles3 = m_groups * n_tiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(K2_CLUSTER3));
+    cfg.blockDim = dim3(K2_THREADS2);
+    cfg.dynamicSmemBytes = K2_SMEM2;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = K2_CLUSTER3;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (attr3_device != dev) {
+      FD_CUDA_OK(cudaFuncSetAttribute(k2_gemm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM2));
+      FD_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, k2_gemm3_kernel, &cfg));
+      attr3_device = dev;
+    }
+    if (max_clusters >= 1) {
+      cfg.gridDim = dim3(static_cast<unsigned>(K2_CLUSTER3 * (tiles3 < max_clusters ? tiles3 : max_clusters)));
+      FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k2_gemm3_kernel, tm_a, tm_b48, tm_b40, tm_out, K, m_groups, n_tiles));
+      return FD_OK;
+    }
+  }
+  if (g_k2_variant >= 2 && m_tiles >= 2 && sms >= 2) {
     // cta_group::2 path: pairs of CTAs own 256 rows (the last pair may be partly or, for an odd number of
     // m tiles, half empty: TMA zero-fills and clips)
     CUtensorMap tm_bh;

@@ -1,5 +1,6 @@
 '''(10 back-to-back launches per graph replay: the first sees a cold L2, the rest a warm one)
-K2 variants (1 = v3 cta_group::1 + multicast pairs, 2 = v4 cta_group::2) against torch.matmul (cuBLAS) on
+K2 variants (1 = v3 cta_group::1 + multicast pairs, 2 = v4 cta_group::2, 3 = v5 six-CTA clusters with the weight tile multicast
+over three pairs when M > 512) against torch.matmul (cuBLAS) on
 the K/V projection shapes: parity, the bounded-wait record, graph-replayed time with a cold L2.'''
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -25,16 +26,17 @@ def timeit(fn, n=10):
 torch.manual_seed(0)
 N, K = 24960, 768
 w = (torch.randn(N, K, device=dev) * K ** -0.5).bfloat16()
-for n_ctx in (1, 2, 3, 9, 17):
+for n_ctx in (9, 17, 1, 2, 3):
     M = n_ctx * 80
     x = torch.randn(M, K, device=dev).bfloat16()
     want = x.float() @ w.float().t()
     row = [f'M={M}']
-    for v in (1, 2):
+    for v in (3, 2, 1):
         lib.fd_debug_set_k2_variant(v)
         out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         _native.kv_project(x, w, out=out); torch.cuda.synchronize()
         err = ((out.float() - want).norm() / want.norm()).item()
+        err = max(err, float((out.float() - want).abs().max() > 0.25))   # any single wrong element shows as >= 1
         flag = lib.fd_debug_k2_flag()
         t = timeit(lambda: _native.kv_project(x, w, out=out))
         row.append(f'v{v}: {t:.1f} us err {err:.1e} flag {flag}')
