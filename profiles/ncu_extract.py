@@ -52,7 +52,7 @@ def main():
         for rec in out:
             name = rec['kernel']
             key = ('k3f' if 'k3f_' in name else 'k3' if 'k3_cross' in name else 'k4' if 'k4_' in name else
-                   'k2' if 'k2_' in name else 'k1' if ('k1_sim' in name or 'k1b_sim' in name) else None)
+                   'k2' if 'k2_' in name else 'k13' if 'k13_' in name else 'k1' if ('k1_sim' in name or 'k1b_sim' in name) else None)
             if key:
                 agg.setdefault(key, []).append(rec.get('dram_rd', 0) + rec.get('dram_wr', 0))
         json.dump({'captured_at': tag, 'source': rep.split('/')[-1],

@@ -96,7 +96,17 @@ def main(mode: str):
     w_fc1, b_fc1 = torch.randn(4096, 1024, device=dev, generator=g) * 0.03, torch.zeros(4096, device=dev)
     w_fc2 = torch.randn(1024, 4096, device=dev, generator=g) * 0.03
 
+    # K13 at bench.py's sample count, one GEGLU projection per width
+    ffs = []
+    for m in picks:
+        C = m.dim
+        ffs.append((torch.randn(S3 * {320: 4096, 640: 1024, 1280: 256}[C], C, device=dev, generator=g).bfloat16(),
+                    (torch.randn(8 * C, C, device=dev, generator=g) * C ** -0.5).bfloat16(),
+                    (torch.randn(8 * C, device=dev, generator=g) * 0.1).bfloat16()))
+
     def run():
+        for xf, wf, bf in ffs:
+            _native.ff_geglu(xf, wf, bf)
         for m, q in zip(picks, qs):
             _native.cross_attn(q, kv.kv, m.k_col_off, m.v_col_off, idx, m.heads, 77, 80,
                                m.scale)
