@@ -15,6 +15,8 @@
 // Tile order: the feature block is the fast index, so the pairs running together share a few 256-row slabs of x (read from
 // HBM once, then L2 hits) and all of W (<= 26 MB, L2-resident).  With m fastest every feature block re-streamed x from HBM
 // while the 4x larger output was flushing the L2: ncu showed 730 MB of DRAM reads for an 84 MB x at C = 320.
+#include <stdlib.h>
+
 #include "fd_common.cuh"
 
 namespace fd {
@@ -60,7 +62,7 @@ __device__ __forceinline__ float gelu_fast(float g) {
 __global__ void __launch_bounds__(G_THREADS, 1)
 k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                     const __grid_constant__ CUtensorMap tm_out, const __nv_bfloat16* __restrict__ bias, int F, int K,
-                    int m_pairs, int f_tiles) {
+                    int m_pairs, int f_tiles, int f_run) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -75,7 +77,11 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = K / G_BK;
-  const int total_tiles = m_pairs * f_tiles;
+  // work item = (256-row block, run of f_run adjacent feature blocks); f_run > 1 only when K = G_STAGES k-blocks, so that
+  // k-block kb always lands in ring stage kb and the x tile can STAY there for the whole run (only W travels)
+  const int f_groups = f_tiles / f_run;
+  const int total_tiles = m_pairs * f_groups;   // work items
+  const bool a_resident = f_run > 1;
   const uint32_t crank = cluster_cta_rank();
   const bool leader = crank == 0;
   const int first_tile = static_cast<int>(blockIdx.x >> 1);
@@ -109,16 +115,22 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     if (elect_one()) {
       int it = 0;
       for (int tile = first_tile; tile < total_tiles; tile += tile_stride) {
-        const int f_blk = tile % f_tiles, m_blk = tile / f_tiles;   // f fastest: see the tile-order note at the top
-        // B rows of this CTA: the value weights (rank 0) or the gate weights (rank 1) of feature block f_blk
-        const int w_row = static_cast<int>(crank) * F + f_blk * G_BF;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % G_STAGES;
-          mbar_wait_bounded(&empty_bar[s], ((it / G_STAGES) & 1) ^ 1, &g_k13_flag, 1);
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * G_STAGE_BYTES);
-          const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[s]), 0);
-          tma_load_2d_2cta(smem + s * G_STAGE_BYTES, &tm_x, lead_bar, kb * G_BK, m_blk * 2 * G_BM + static_cast<int>(crank) * G_BM);
-          tma_load_2d_2cta(smem + s * G_STAGE_BYTES + G_A_BYTES, &tm_w, lead_bar, kb * G_BK, w_row);
+        const int m_blk = tile / f_groups;   // the feature run is the fast index: see the tile-order note at the top
+        for (int j = 0; j < f_run; ++j) {
+          const int f_blk = (tile % f_groups) * f_run + j;
+          // B rows of this CTA: the value weights (rank 0) or the gate weights (rank 1) of feature block f_blk
+          const int w_row = static_cast<int>(crank) * F + f_blk * G_BF;
+          const bool load_a = !a_resident || j == 0;
+          for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int s = it % G_STAGES;
+            mbar_wait_bounded(&empty_bar[s], ((it / G_STAGES) & 1) ^ 1, &g_k13_flag, 1);
+            if (leader) mbar_expect_tx(&full_bar[s], load_a ? 2 * G_STAGE_BYTES : 2 * G_B_BYTES);
+            const uint32_t lead_bar = mapa_rank(smem_u32(&full_bar[s]), 0);
+            if (load_a)
+              tma_load_2d_2cta(smem + s * G_STAGE_BYTES, &tm_x, lead_bar, kb * G_BK,
+                               m_blk * 2 * G_BM + static_cast<int>(crank) * G_BM);
+            tma_load_2d_2cta(smem + s * G_STAGE_BYTES + G_A_BYTES, &tm_w, lead_bar, kb * G_BK, w_row);
+          }
         }
       }
     }
@@ -126,7 +138,8 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     if (leader && elect_one()) {
       constexpr uint32_t idesc = umma_idesc(UMMA_BF16, 2 * G_BM, G_BN, 0, 0);
       int it = 0, local = 0;
-      for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_stride)
+      for (int j = 0; j < f_run; ++j, ++local) {
         const int acc = local & 1;
         mbar_wait_bounded(&tmem_empty[acc], ((local >> 1) & 1) ^ 1, &g_k13_flag, 2);  // both epilogues drained it
         tc_fence_after();
@@ -156,8 +169,9 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
     const bool issuer = et % 128 == 0;                  // first thread of each half
     uint8_t* my_stage = out_stage + half * 2 * G_OUT_CHUNK;
     int local = 0;
-    for (int tile = first_tile; tile < total_tiles; tile += tile_stride, ++local) {
-      const int f_blk = tile % f_tiles, m_blk = tile / f_tiles;   // f fastest: see the tile-order note at the top
+    for (int tile = first_tile; tile < total_tiles; tile += tile_stride)
+    for (int j = 0; j < f_run; ++j, ++local) {
+      const int m_blk = tile / f_groups, f_blk = (tile % f_groups) * f_run + j;
       const int acc = local & 1;
       // this half's biases of the tile as fp32: 64 value + 64 gate, one per thread of the half.  Single-buffered: a thread
       // gets here only after the half's second named barrier of the previous tile, i.e. after every read of the old
@@ -277,7 +291,24 @@ extern "C" int fd_ff_geglu(const void* x_bf16_dev, const void* w_bf16_dev, const
     attr_device = dev;
   }
   const int m_pairs = (M + 2 * G_BM - 1) / (2 * G_BM), f_tiles = F / G_BF;
-  const int tiles = m_pairs * f_tiles, max_pairs = sms / 2;
+  const int max_pairs = sms / 2;
+  // feature blocks per work item (x tile resident for the run): only when K is exactly G_STAGES k-blocks (C = 320, the sites
+  // with the most rows, which are otherwise bound by the bytes crossing L2 -> SM: 128 flop per byte at K = 320).  Pick the
+  // divisor of f_tiles with the fewest estimated tile-times (measured: a tile with its x resident is ~7 % shorter, 208 -> 194 us
+  // at 32 samples; fewer, longer work items also remove a partial wave at small M: 19.1 -> 18.2 us at 2 samples).
+  int f_run = 1;
+  if (K == G_STAGES * G_BK) {
+    static const int forced = [] { const char* e = getenv("FD_K13_FRUN"); return e ? atoi(e) : 0; }();
+    double best = 1e30;
+    for (int r = 1; r <= f_tiles; ++r) {
+      if (f_tiles % r) continue;
+      const long items = static_cast<long>(m_pairs) * (f_tiles / r);
+      const double cost = static_cast<double>((items + max_pairs - 1) / max_pairs) * r * (1.0 - 0.07 * (1.0 - 1.0 / r));
+      if (cost < best - 1e-9) { best = cost; f_run = r; }
+    }
+    if (forced > 0 && f_tiles % forced == 0) f_run = forced;
+  }
+  const int tiles = m_pairs * (f_tiles / f_run);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(2 * (tiles < max_pairs ? tiles : max_pairs)));
   cfg.blockDim = dim3(G_THREADS);
@@ -291,7 +322,7 @@ extern "C" int fd_ff_geglu(const void* x_bf16_dev, const void* w_bf16_dev, const
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k13_ff_geglu_kernel, tm_x, tm_w, tm_out, static_cast<const __nv_bfloat16*>(bias_bf16_dev), F,
-                                K, m_pairs, f_tiles));
+                                K, m_pairs, f_tiles, f_run));
   return FD_OK;
 }
 
