@@ -36,11 +36,16 @@ def _resized_rgb(image: Any) -> np.ndarray:
     return np.array(image.resize((w, h), resample=LANCZOS).convert('RGB'))
 
 
+# clip.py:37-39 computes `2.0 * (uint8.astype(float32) / 255.0) - 1.0` (numpy division, torch multiply / subtract) over the
+# whole image in three passes; the same three float32 operations on the 256 possible byte values, then one gather, give
+# the identical bits with one pass over the pixels (`Guide.embeds` is bounded by this host work + the vision tower)
+_PIXEL_LUT = (2.0 * torch.from_numpy(np.arange(256).astype(np.float32) / 255.0) - 1.0).numpy()
+
+
 def preprocess(image: Any) -> torch.Tensor:
     '''PIL image -> [1,3,h,w] float32 in [-1,1]; the longer side becomes 512, the
     shorter one is scaled with it and floored to a multiple of 64 (clip.py:24-39).'''
-    arr = _resized_rgb(image).astype(np.float32) / 255.0
-    return 2.0 * torch.from_numpy(arr[None].transpose(0, 3, 1, 2)) - 1.0
+    return torch.from_numpy(np.take(_PIXEL_LUT, _resized_rgb(image))[None].transpose(0, 3, 1, 2))
 
 
 class _TowerGraph:
@@ -151,9 +156,6 @@ def _x3_encoder(encoder, hidden: torch.Tensor, causal: bool) -> torch.Tensor:
             h = mlp.activation_fn(h)
         hidden = _native.linear_x3(h, mlp.fc2.weight, mlp.fc2.bias, residual=hidden)           # x + mlp(ln2(x))
     return hidden.view(B, T, C)
-
-
-    return hidden
 
 
 class CLIPEncoder():
