@@ -30,6 +30,31 @@ def test_ff_geglu_matches_fp32(native, cuda_dev, M, C):
     assert torch.equal(got3.view(M, 4 * C), got)
 
 
+def test_ff_geglu_gate_range(native, cuda_dev):
+    '''The epilogue's gelu is `g * 2^p(|g|)` (a fit of log2 Phi(-a) on [0, 6.72], clamped at 11): drive the gate through
+    [-60, 60], zeros and tiny values with an identity-like projection and compare with F.gelu on the same bf16 gates.
+    Tolerance: one bf16 ulp of the result (2^-8 relative) plus 1e-6 absolute for the far negative tail.'''
+    C = 320
+    F_ = 4 * C
+    w = torch.zeros(2 * F_, C, device=cuda_dev)
+    idx = torch.arange(F_, device=cuda_dev)
+    w[idx, idx % C] = 1.0                 # value[f] = x[f % C]
+    w[F_ + idx, (idx + 1) % C] = 1.0      # gate[f]  = x[(f + 1) % C]
+    gates = torch.cat([torch.linspace(-60, 60, 257), torch.tensor([0.0, -0.0, 1e-30, -1e-30, 1e-4, -1e-4]),
+                       torch.linspace(-8, 8, 57)]).to(cuda_dev)
+    x = torch.empty(256, C, device=cuda_dev)
+    for r in range(256):
+        x[r] = gates.roll(r)
+    x = x.bfloat16()
+    got = native.ff_geglu(x, w.bfloat16(), torch.zeros(2 * F_, device=cuda_dev).bfloat16()).float()
+    xf = x.float()
+    want = xf[:, idx % C] * F.gelu(xf[:, (idx + 1) % C].double()).float()
+    assert torch.isfinite(got).all()
+    err = (got - want).abs()
+    assert (err <= want.abs() * 2.0 ** -8 + 1e-6).all(), float((err - want.abs() * 2.0 ** -8).max())
+    assert native.lib().fd_debug_k13_flag() == 0
+
+
 def test_ff_geglu_rejects_bad_shapes(native, cuda_dev):
     x = torch.randn(64, 96, device=cuda_dev).bfloat16()
     with pytest.raises(native.NativeError):
