@@ -463,18 +463,19 @@ def geglu(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def add_bias_residual(x: torch.Tensor, h: torch.Tensor,
-                      bias: torch.Tensor) -> torch.Tensor:
-    '''fd_add_bias_residual: x + h + bias[c] on channels-last bf16 [N,C,H,W] tensors.'''
+def add_bias_residual(x: torch.Tensor, h: Optional[torch.Tensor],
+                      bias: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    '''fd_add_bias_residual: x + h + bias[c] on channels-last bf16 [N,C,H,W] tensors; h None: x + bias[c]
+    (`inplace`: written over x when x is already channels-last).'''
     for name, t in (('x', x), ('h', h)):
-        if t.dtype != torch.bfloat16 or not t.is_cuda:
+        if t is not None and (t.dtype != torch.bfloat16 or not t.is_cuda):
             raise NativeError(f'{name} must be CUDA bfloat16; no fallback')
     if not x.is_contiguous(memory_format=torch.channels_last):
         x = x.contiguous(memory_format=torch.channels_last)
-    if not h.is_contiguous(memory_format=torch.channels_last):
+    if h is not None and not h.is_contiguous(memory_format=torch.channels_last):
         h = h.contiguous(memory_format=torch.channels_last)
     _need(bias, 'bias', torch.bfloat16)
-    y = torch.empty_like(x)
+    y = x if inplace else torch.empty_like(x)
     rc = lib().fd_add_bias_residual(ptr(x), ptr(h), ptr(bias), ptr(y), x.numel(),
                                     x.shape[1], stream_ptr(x.device))
     check(rc, 'fd_add_bias_residual')

@@ -279,13 +279,22 @@ class SpatialTransformer(nn.Module):
         return h.reshape(B, H, W, C).permute(0, 3, 1, 2) + x
 
 
+def _conv_bias(x, conv: nn.Conv2d, stride: int = 1):
+    '''3x3 convolution with its bias added by K7 (h = None) instead of ATen's broadcasting add kernel.'''
+    if (conv.bias is None or not x.is_cuda or x.dtype != torch.bfloat16 or conv.out_channels % 8
+            or conv.bias.dtype != torch.bfloat16):
+        return conv(x)
+    h = F.conv2d(x, conv.weight, None, stride=stride, padding=conv.padding)
+    return _native.add_bias_residual(h, None, conv.bias, inplace=True)
+
+
 class Downsample2D(nn.Module):
     def __init__(self, ch: int):
         super().__init__()
         self.conv = nn.Conv2d(ch, ch, 3, stride=2, padding=1)
 
     def forward(self, x):
-        return self.conv(x)
+        return _conv_bias(x, self.conv, stride=2)
 
 
 class Upsample2D(nn.Module):
@@ -294,7 +303,7 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
     def forward(self, x):
-        return self.conv(F.interpolate(x, scale_factor=2.0, mode='nearest'))
+        return _conv_bias(F.interpolate(x, scale_factor=2.0, mode='nearest'), self.conv)
 
 
 class DownBlock(nn.Module):
@@ -521,7 +530,7 @@ class UNet2DConditionModel(nn.Module):
                 self._tb_weight.device == emb.device and self._tb_weight.dtype == emb.dtype:
             emb = TembBank(F.linear(emb, self._tb_weight, self._tb_bias), self._tb_slices)
 
-        x = self.conv_in(sample.to(dtype))
+        x = _conv_bias(sample.to(dtype), self.conv_in)
         skips = [x]
         for blk in self.down_blocks:
             x, outs = blk(x, emb, kv_cache, ctx_index)

@@ -343,8 +343,9 @@ int fd_groupnorm_act(const void* x_bf16_dev,     /* [N, HW, C] channels-last act
                      int64_t bias_row_stride,    /* elements between bias rows (>= C, even) */
                      void* stream);
 
-/* y = x + h + bias[c]: ResnetBlock2D's residual add with conv2's bias folded in (NHWC bf16). */
-int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev,
+/* y = x + h + bias[c]: ResnetBlock2D's residual add with conv2's bias folded in (NHWC bf16).
+ * h == NULL: y = x + bias[c] (the bias of conv_in / Downsample2D / Upsample2D convolutions); y may alias x. */
+int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev /* or NULL */,
                          const void* bias_bf16_dev,  /* [C]                                 */
                          void* y_bf16_dev, int64_t n_elem, int C, void* stream);
 

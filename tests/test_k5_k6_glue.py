@@ -70,6 +70,12 @@ def test_add_bias_residual_matches_torch(native, cuda_dev, N, C, H, W):
     ref = x.float() + (h.float() + b.float()[None, :, None, None])
     assert y.is_contiguous(memory_format=torch.channels_last)
     torch.testing.assert_close(y.float(), ref, rtol=1e-2, atol=1e-2)
+    # h = None: the plain convolution-bias add (conv_in / Downsample2D / Upsample2D), bit-equal to torch's bf16 add, also in place
+    want = x + b[None, :, None, None]
+    assert torch.equal(native.add_bias_residual(x, None, b), want)
+    x2 = x.clone(memory_format=torch.preserve_format)
+    assert native.add_bias_residual(x2, None, b, inplace=True).data_ptr() == x2.data_ptr()
+    assert torch.equal(x2, want)
 
 
 def test_groupnorm_is_bit_reproducible(native, cuda_dev):
