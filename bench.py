@@ -419,7 +419,16 @@ def kernel_rooflines(dev, unet, peaks):
                      blends_per_s=nb / t, issued_fp16_tflops=fl / t / 1e12,
                      tokens_reweighted_by_cluster_or_threshold=n_guided, prompts_flagged=n_flagged,
                      avg_launch_us=t * 1e6, peak_of=peaks['source'])
-    del txt, img
+    # the same launch at 4096 prompts: 1024 prompts are 6.9 per persistent CTA, i.e. three two-prompt batches and a single
+    # (four batch slots for 3.46 batches of work); 4096 amortise that quantisation
+    txt4 = txt.repeat(4, 1, 1)
+    f4 = lambda: _native.sim_blend(txt4, img, [prm], lin)
+    f4()
+    t4 = _time_cuda(f4, 3)
+    by4 = 4 * nb * (2 * 77 * 768 * 4) + 257 * 768 * 4
+    out['k1']['at_4096_prompts'] = dict(avg_launch_us=t4 * 1e6, blends_per_s=4 * nb / t4, achieved=by4 / t4 / 1e9,
+                                        frac=by4 / t4 / 1e9 / peaks['hbm'])
+    del txt, img, txt4, f4
     # ---- K5 (GroupNorm + bias + SiLU glue): by time the largest hand-written kernel of a step, so
     # it is reported too: every (N=2, C, H, W) call of one UNet forward, graph-replayed on its own
     # L2-resident input, as in situ where the producer convolution has just written it
