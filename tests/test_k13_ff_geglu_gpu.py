@@ -8,7 +8,8 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('M,C', [(8192, 320), (2048, 640), (512, 1280), (128, 1280), (1000, 320), (300, 640)])
+@pytest.mark.parametrize('M,C', [(8192, 320), (2048, 640), (512, 1280), (128, 1280), (1000, 320), (300, 640),
+                                  (40000, 320)])   # (40000, 320): resident-x feature runs with a ragged last row block
 def test_ff_geglu_matches_fp32(native, cuda_dev, M, C):
     g = torch.Generator(device=cuda_dev).manual_seed(M + C)
     x = torch.randn(M, C, device=cuda_dev, generator=g).bfloat16()
