@@ -34,7 +34,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
                'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3_split_ln', 'fd_linear_x3',
                'fd_linear_x3_flag',
-               'fd_attention_f32', 'fd_ff_geglu')
+               'fd_attention_f32', 'fd_ff_geglu', 'fd_concat_channels')
 
 
 class NativeError(RuntimeError):
@@ -156,6 +156,8 @@ def lib() -> C.CDLL:
     l.fd_attention_f32.restype = C.c_int
     l.fd_ff_geglu.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
     l.fd_ff_geglu.restype = C.c_int
+    l.fd_concat_channels.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
+    l.fd_concat_channels.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -479,6 +481,25 @@ def add_bias_residual(x: torch.Tensor, h: Optional[torch.Tensor],
     rc = lib().fd_add_bias_residual(ptr(x), ptr(h), ptr(bias), ptr(y), x.numel(),
                                     x.shape[1], stream_ptr(x.device))
     check(rc, 'fd_add_bias_residual')
+    count_launch()
+    return y
+
+
+def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    '''fd_concat_channels: torch.cat([a, b], dim=1) for channels-last bf16 [N,C,H,W] tensors (C % 8 == 0).'''
+    for name, t in (('a', a), ('b', b)):
+        if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+            raise NativeError(f'{name} must be a CUDA bfloat16 [N,C,H,W] tensor; no fallback')
+    if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+        raise NativeError(f'concat_channels: shapes {tuple(a.shape)} and {tuple(b.shape)} do not match')
+    if not a.is_contiguous(memory_format=torch.channels_last):
+        a = a.contiguous(memory_format=torch.channels_last)
+    if not b.is_contiguous(memory_format=torch.channels_last):
+        b = b.contiguous(memory_format=torch.channels_last)
+    N, Ca, H, W = a.shape
+    Cb = b.shape[1]
+    y = torch.empty((N, Ca + Cb, H, W), dtype=torch.bfloat16, device=a.device, memory_format=torch.channels_last)
+    check(lib().fd_concat_channels(ptr(a), ptr(b), ptr(y), N * H * W, Ca, Cb, stream_ptr(a.device)), 'fd_concat_channels')
     count_launch()
     return y
 

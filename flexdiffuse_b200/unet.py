@@ -288,6 +288,14 @@ def _conv_bias(x, conv: nn.Conv2d, stride: int = 1):
     return _native.add_bias_residual(h, None, conv.bias, inplace=True)
 
 
+def _cat_skip(x, skip):
+    '''torch.cat([x, skip], dim=1) through K15 on channels-last bf16 activations.'''
+    if (x.is_cuda and x.dtype == torch.bfloat16 and skip.dtype == torch.bfloat16 and x.shape[1] % 8 == 0
+            and skip.shape[1] % 8 == 0):
+        return _native.concat_channels(x, skip)
+    return torch.cat([x, skip], dim=1)
+
+
 class Downsample2D(nn.Module):
     def __init__(self, ch: int):
         super().__init__()
@@ -369,7 +377,7 @@ class UpBlock(nn.Module):
 
     def forward(self, x, skips: List[torch.Tensor], temb, kv, ctx_index):
         for i, res in enumerate(self.resnets):
-            x = res(torch.cat([x, skips.pop()], dim=1), temb)
+            x = res(_cat_skip(x, skips.pop()), temb)
             if self.attentions is not None:
                 x = self.attentions[i](x, kv, ctx_index)
         if self.upsamplers is not None:

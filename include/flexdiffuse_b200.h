@@ -349,6 +349,14 @@ int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev /* or NU
                          const void* bias_bf16_dev,  /* [C]                                 */
                          void* y_bf16_dev, int64_t n_elem, int C, void* stream);
 
+/* y[p, 0:Ca] = a[p, :], y[p, Ca:Ca+Cb] = b[p, :] on channels-last bf16 tensors: the skip-connection
+ * `torch.cat([hidden, skip], dim=1)` of diffusers' up blocks inside the UNet call at pipeline/guide.py:56-58. */
+int fd_concat_channels(const void* a_bf16_dev,   /* [pixels, Ca]                           */
+                       const void* b_bf16_dev,   /* [pixels, Cb]                           */
+                       void* y_bf16_dev,         /* [pixels, Ca + Cb]                      */
+                       int64_t pixels, int Ca, int Cb, /* Ca % 8 == 0, Cb % 8 == 0         */
+                       void* stream);
+
 /* s = x + y ; n = LayerNorm(s) * gamma + beta   (BasicTransformerBlock: the residual add of one
  * attention / feed-forward branch fused with the LayerNorm feeding the next one).  y == NULL:
  * plain LayerNorm of x.  Rows of C in {320, 640, 1280} bf16.                                 */

@@ -47,5 +47,22 @@ def main():
               f'torch GroupNorm+SiLU {t_ref:7.2f} us')
 
 
+def cat_main():
+    '''K15 against torch.cat on the up blocks' skip concats (channels-last bf16), N = 2 and 16 samples.'''
+    dev = torch.device('cuda:0')
+    for N in (2, 16):
+        for Ca, Cb, H in ((1280, 1280, 8), (1280, 1280, 16), (1280, 640, 16), (1280, 640, 32), (640, 640, 32), (640, 320, 32),
+                          (640, 320, 64), (320, 320, 64)):
+            a = torch.randn(N, Ca, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+            b = torch.randn(N, Cb, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+            t = graph_time(lambda: _native.concat_channels(a, b))
+            t_ref = graph_time(lambda: torch.cat([a, b], dim=1))
+            mb = 2 * (a.numel() + b.numel()) * 2 / 1e6
+            print(f'K15 N={N} {Ca}+{Cb} {H}x{H}: {t:7.2f} us ({mb / t * 1e6 / 1e6:5.2f} TB/s r+w)   torch.cat {t_ref:7.2f} us')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'cat':
+        cat_main()
+        sys.exit(0)
     main()

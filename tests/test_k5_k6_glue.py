@@ -78,6 +78,16 @@ def test_add_bias_residual_matches_torch(native, cuda_dev, N, C, H, W):
     assert torch.equal(x2, want)
 
 
+@pytest.mark.parametrize('N,Ca,Cb,H', [(2, 640, 320, 64), (2, 1280, 1280, 8), (3, 320, 320, 17), (16, 640, 320, 64)])
+def test_concat_channels_equals_torch_cat(native, cuda_dev, N, Ca, Cb, H):
+    g = torch.Generator(device=cuda_dev).manual_seed(Ca + Cb)
+    a = torch.randn(N, Ca, H, H, device=cuda_dev, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(N, Cb, H, H, device=cuda_dev, generator=g).bfloat16()   # NCHW-contiguous: converted on the way in
+    y = native.concat_channels(a, b)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y, torch.cat([a, b], dim=1))
+
+
 def test_groupnorm_is_bit_reproducible(native, cuda_dev):
     x = torch.randn(2, 640, 32, 32, device=cuda_dev).bfloat16() \
         .contiguous(memory_format=torch.channels_last)
