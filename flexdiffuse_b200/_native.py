@@ -34,7 +34,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
                'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3_split_ln', 'fd_linear_x3',
                'fd_linear_x3_flag',
-               'fd_attention_f32', 'fd_ff_geglu', 'fd_concat_channels')
+               'fd_attention_f32', 'fd_ff_geglu', 'fd_concat_channels', 'fd_upsample_nearest2x')
 
 
 class NativeError(RuntimeError):
@@ -158,6 +158,8 @@ def lib() -> C.CDLL:
     l.fd_ff_geglu.restype = C.c_int
     l.fd_concat_channels.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
     l.fd_concat_channels.restype = C.c_int
+    l.fd_upsample_nearest2x.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp]
+    l.fd_upsample_nearest2x.restype = C.c_int
     l.fd_image_tail_u8.argtypes = [vp, C.c_int, C.c_int64, vp, vp]
     l.fd_image_tail_u8.restype = C.c_int
     l.fd_geglu.argtypes = [vp, vp, C.c_int64, C.c_int, vp]
@@ -500,6 +502,19 @@ def concat_channels(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     Cb = b.shape[1]
     y = torch.empty((N, Ca + Cb, H, W), dtype=torch.bfloat16, device=a.device, memory_format=torch.channels_last)
     check(lib().fd_concat_channels(ptr(a), ptr(b), ptr(y), N * H * W, Ca, Cb, stream_ptr(a.device)), 'fd_concat_channels')
+    count_launch()
+    return y
+
+
+def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
+    '''fd_upsample_nearest2x: F.interpolate(x, scale_factor=2.0, mode='nearest') for a channels-last bf16 [N,C,H,W] tensor.'''
+    if x.dtype != torch.bfloat16 or not x.is_cuda or x.dim() != 4:
+        raise NativeError('upsample_nearest2x needs a CUDA bfloat16 [N,C,H,W] tensor; no fallback')
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    N, Cc, H, W = x.shape
+    y = torch.empty((N, Cc, 2 * H, 2 * W), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+    check(lib().fd_upsample_nearest2x(ptr(x), ptr(y), N, H, W, Cc, stream_ptr(x.device)), 'fd_upsample_nearest2x')
     count_launch()
     return y
 

@@ -357,6 +357,11 @@ int fd_concat_channels(const void* a_bf16_dev,   /* [pixels, Ca]                
                        int64_t pixels, int Ca, int Cb, /* Ca % 8 == 0, Cb % 8 == 0         */
                        void* stream);
 
+/* Nearest-neighbour 2x upsample, channels-last bf16 [N,H,W,C] -> [N,2H,2W,C]: `F.interpolate(x, scale_factor=2.0,
+ * mode="nearest")` of diffusers' Upsample2D inside the UNet call at pipeline/guide.py:56-58. */
+int fd_upsample_nearest2x(const void* x_bf16_dev, void* y_bf16_dev, int N, int H, int W,
+                          int C /* % 8 == 0 */, void* stream);
+
 /* s = x + y ; n = LayerNorm(s) * gamma + beta   (BasicTransformerBlock: the residual add of one
  * attention / feed-forward branch fused with the LayerNorm feeding the next one).  y == NULL:
  * plain LayerNorm of x.  Rows of C in {320, 640, 1280} bf16.                                 */

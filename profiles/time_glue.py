@@ -61,7 +61,20 @@ def cat_main():
             print(f'K15 N={N} {Ca}+{Cb} {H}x{H}: {t:7.2f} us ({mb / t * 1e6 / 1e6:5.2f} TB/s r+w)   torch.cat {t_ref:7.2f} us')
 
 
+def up_main():
+    dev = torch.device('cuda:0')
+    for N in (2, 16):
+        for C, H in ((1280, 8), (1280, 16), (640, 32)):
+            x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(memory_format=torch.channels_last)
+            t = graph_time(lambda: _native.upsample_nearest2x(x))
+            t_ref = graph_time(lambda: F.interpolate(x, scale_factor=2.0, mode='nearest'))
+            print(f'K15 upsample N={N} C={C} {H}x{H}: {t:7.2f} us ({5 * x.numel() * 2 / t / 1e6:5.2f} TB/s r+w)   F.interpolate {t_ref:7.2f} us')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'up':
+        up_main()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'cat':
         cat_main()
         sys.exit(0)

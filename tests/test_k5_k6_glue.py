@@ -88,6 +88,14 @@ def test_concat_channels_equals_torch_cat(native, cuda_dev, N, Ca, Cb, H):
     assert torch.equal(y, torch.cat([a, b], dim=1))
 
 
+@pytest.mark.parametrize('N,C,H,W', [(2, 1280, 8, 8), (2, 640, 32, 32), (3, 320, 5, 9), (16, 640, 32, 32)])
+def test_upsample_nearest2x_equals_interpolate(native, cuda_dev, N, C, H, W):
+    x = torch.randn(N, C, H, W, device=cuda_dev).bfloat16().contiguous(memory_format=torch.channels_last)
+    y = native.upsample_nearest2x(x)
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(y, F.interpolate(x, scale_factor=2.0, mode='nearest'))
+
+
 def test_groupnorm_is_bit_reproducible(native, cuda_dev):
     x = torch.randn(2, 640, 32, 32, device=cuda_dev).bfloat16() \
         .contiguous(memory_format=torch.channels_last)
