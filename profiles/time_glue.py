@@ -34,6 +34,7 @@ def main():
     dev = torch.device('cuda:0')
     for (N, C, H) in [(2, 320, 64), (2, 640, 64), (2, 960, 64), (2, 640, 32), (2, 1280, 32),
                       (2, 1920, 32), (2, 1280, 16), (2, 2560, 16), (2, 1280, 8), (2, 2560, 8),
+                      (16, 320, 64), (16, 640, 64), (16, 960, 64), (16, 640, 32), (16, 1280, 32), (16, 1280, 16), (16, 2560, 16),
                       (32, 320, 64), (1, 128, 512)]:
         x = torch.randn(N, C, H, H, device=dev).bfloat16().contiguous(
             memory_format=torch.channels_last)
