@@ -993,10 +993,14 @@ def main():
         line['roofline_k1'] = kr['k1']
         line['roofline_k5'] = kr['k5']
         line['roofline_k13'] = kr['k13']
+        # the microbenchmarks leave several GB of freed blocks in the caching allocator; hand them back so the configs below
+        # start from a clean pool (config 3's single timed step varied 14.7 -> 11.5 images/s with the pool's history)
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and extras:
         # the other single-GPU BASELINE configs, the torch GPU baseline and the CPU baselines: N = 1 only
-        line['other_configs'] = {'config2': run_config2(dev, pipe_factory, unet),
-                                 'config3': run_config3(dev, pipe_factory, unet)}
+        line['other_configs'] = {'config2': run_config2(dev, pipe_factory, unet, steps=1, warmup=2),
+                                 'config3': run_config3(dev, pipe_factory, unet, steps=1, warmup=2)}
         line['gpu_torch_baseline'] = gpu_torch_baseline(dev, unet, vae, d_uncond, d_embeds)
         line['gpu_torch_baseline']['speedup_resident_vs_eager'] = value / line['gpu_torch_baseline']['eager_images_per_s']
         line['gpu_torch_baseline']['speedup_resident_vs_cuda_graph'] = (

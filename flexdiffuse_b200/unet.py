@@ -19,6 +19,8 @@ import math
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -279,9 +281,13 @@ class SpatialTransformer(nn.Module):
         return h.reshape(B, H, W, C).permute(0, 3, 1, 2) + x
 
 
+# development A/B switch: FD_ATEN_GLUE=1 sends the convolution-bias adds, the skip concats and the nearest upsamples back to ATen
+NATIVE_GLUE = os.environ.get('FD_ATEN_GLUE', '0') != '1'
+
+
 def _conv_bias(x, conv: nn.Conv2d, stride: int = 1):
     '''3x3 convolution with its bias added by K7 (h = None) instead of ATen's broadcasting add kernel.'''
-    if (conv.bias is None or not x.is_cuda or x.dtype != torch.bfloat16 or conv.out_channels % 8
+    if (not NATIVE_GLUE or conv.bias is None or not x.is_cuda or x.dtype != torch.bfloat16 or conv.out_channels % 8
             or conv.bias.dtype != torch.bfloat16):
         return conv(x)
     h = F.conv2d(x, conv.weight, None, stride=stride, padding=conv.padding)
@@ -290,7 +296,7 @@ def _conv_bias(x, conv: nn.Conv2d, stride: int = 1):
 
 def _cat_skip(x, skip):
     '''torch.cat([x, skip], dim=1) through K15 on channels-last bf16 activations.'''
-    if (x.is_cuda and x.dtype == torch.bfloat16 and skip.dtype == torch.bfloat16 and x.shape[1] % 8 == 0
+    if (NATIVE_GLUE and x.is_cuda and x.dtype == torch.bfloat16 and skip.dtype == torch.bfloat16 and x.shape[1] % 8 == 0
             and skip.shape[1] % 8 == 0):
         return _native.concat_channels(x, skip)
     return torch.cat([x, skip], dim=1)
@@ -311,7 +317,7 @@ class Upsample2D(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
     def forward(self, x):
-        if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        if NATIVE_GLUE and x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
             return _conv_bias(_native.upsample_nearest2x(x), self.conv)   # K15
         return _conv_bias(F.interpolate(x, scale_factor=2.0, mode='nearest'), self.conv)
 

@@ -10,6 +10,8 @@ from __future__ import annotations
 from dataclasses import dataclass
 from typing import Optional
 
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -84,7 +86,8 @@ class _Up(nn.Module):
         self.conv = nn.Conv2d(ch, ch, 3, padding=1)
 
     def forward(self, x):
-        if x.is_cuda and x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+        if (os.environ.get('FD_ATEN_GLUE', '0') != '1' and x.is_cuda and x.dtype == torch.bfloat16
+                and x.shape[1] % 8 == 0):
             return self.conv(_native.upsample_nearest2x(x))   # K15 (ATen's nhwc nearest kernel moves < 1 TB/s)
         return self.conv(F.interpolate(x, scale_factor=2.0, mode='nearest'))
 
