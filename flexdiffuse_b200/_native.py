@@ -16,7 +16,7 @@ import torch
 LIB_NAME = 'libflexdiffuse_b200.so'
 LIB_PATH = Path(__file__).resolve().parent / LIB_NAME
 
-FD_ABI_VERSION = 3
+FD_ABI_VERSION = 4
 FD_DTYPE_F32 = 0
 FD_DTYPE_BF16 = 1
 FD_BLEND_OK = 0
@@ -132,7 +132,7 @@ def lib() -> C.CDLL:
     ]
     l.fd_groupnorm_act.restype = C.c_int
     l.fd_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int,
-                                   C.c_float, vp]
+                                   C.c_float, C.c_int64, vp]
     l.fd_add_layernorm.restype = C.c_int
     l.fd_composite_eps.argtypes = [vp, C.c_int, C.POINTER(EntityBox), C.c_int, C.c_int,
                                    C.c_int, C.c_int, vp, vp, vp]
@@ -154,7 +154,7 @@ def lib() -> C.CDLL:
     l.fd_attention_f32.argtypes = [vp, vp, vp, C.c_int64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                    C.c_int, vp]
     l.fd_attention_f32.restype = C.c_int
-    l.fd_ff_geglu.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp]
+    l.fd_ff_geglu.argtypes = [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int64, vp]
     l.fd_ff_geglu.restype = C.c_int
     l.fd_concat_channels.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp]
     l.fd_concat_channels.restype = C.c_int
@@ -519,20 +519,35 @@ def upsample_nearest2x(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def _column_block(t: torch.Tensor, rows: int, cols: int, name: str) -> int:
+    '''Row stride (elements) of `t`, a [rows, cols] bf16 column block of a wider row-major matrix.'''
+    if (t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 2 or tuple(t.shape) != (rows, cols) or t.stride(1) != 1
+            or t.stride(0) < cols or t.data_ptr() % 16):
+        raise NativeError(f'{name} must be a CUDA bfloat16 [{rows}, {cols}] view with unit column stride, 16-byte aligned')
+    return t.stride(0)
+
+
 def add_layernorm(x: torch.Tensor, y: Optional[torch.Tensor], gamma: torch.Tensor,
-                  beta: torch.Tensor, eps: float):
-    '''fd_add_layernorm.  Returns (x + y, LayerNorm(x + y)); with y None: (x, LayerNorm(x)).'''
+                  beta: torch.Tensor, eps: float, sum_out: Optional[torch.Tensor] = None):
+    '''fd_add_layernorm.  Returns (x + y, LayerNorm(x + y)); with y None: (x, LayerNorm(x)).  `sum_out`: a [M, C]
+    column block of a wider matrix to receive x + y instead of a fresh tensor.'''
     _need(x, 'x', torch.bfloat16)
     Cc = x.shape[-1]
     norm = torch.empty_like(x)
-    total = None
+    total, stride = None, 0
     if y is not None:
         _need(y, 'y', torch.bfloat16)
         if y.shape != x.shape:
             raise NativeError('x / y shape mismatch')
-        total = torch.empty_like(x)
+        if sum_out is not None:
+            stride = _column_block(sum_out, x.numel() // Cc, Cc, 'sum_out')
+            total = sum_out
+        else:
+            total = torch.empty_like(x)
+    elif sum_out is not None:
+        raise NativeError('add_layernorm: sum_out without y')
     rc = lib().fd_add_layernorm(ptr(x), ptr(y), ptr(gamma), ptr(beta), ptr(total),
-                                ptr(norm), x.numel() // Cc, Cc, float(eps),
+                                ptr(norm), x.numel() // Cc, Cc, float(eps), stride,
                                 stream_ptr(x.device))
     check(rc, 'fd_add_layernorm')
     count_launch()
@@ -722,9 +737,10 @@ def attention_f32(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int,
 
 
 # --------------------------------------------------------------------------- K13
-def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     '''fd_ff_geglu: x [..., K] bf16, weight [2F, K] bf16 (value rows, gate rows), bias [2F] bf16 ->
-    (x W_v^T + b_v) * gelu(x W_g^T + b_g) as [..., F] bf16; the [.., 2F] projection is never materialised.'''
+    (x W_v^T + b_v) * gelu(x W_g^T + b_g) as [..., F] bf16; the [.., 2F] projection is never materialised.
+    `out`: a [M, F] column block of a wider matrix to write into (returned as is).'''
     _need(weight, 'weight', torch.bfloat16)
     _need(bias, 'bias', torch.bfloat16)
     if not x.is_cuda or x.dtype != torch.bfloat16:
@@ -736,10 +752,17 @@ def ff_geglu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch
     F2 = weight.shape[0]
     if weight.shape[1] != K or F2 % 2 or bias.numel() != F2:
         raise NativeError(f'ff_geglu: weight {tuple(weight.shape)} / bias {tuple(bias.shape)} do not fit K={K}')
-    out = torch.empty((M, F2 // 2), dtype=torch.bfloat16, device=x.device)
-    check(lib().fd_ff_geglu(ptr(x2), ptr(weight), ptr(bias), ptr(out), M, F2 // 2, K, stream_ptr(x.device)), 'fd_ff_geglu')
+    stride = 0
+    if out is not None:
+        stride = _column_block(out, M, F2 // 2, 'out')
+        if stride % 8:
+            raise NativeError('ff_geglu: output row stride must be a multiple of 8 elements')
+    else:
+        out = torch.empty((M, F2 // 2), dtype=torch.bfloat16, device=x.device)
+    check(lib().fd_ff_geglu(ptr(x2), ptr(weight), ptr(bias), ptr(out), M, F2 // 2, K, stride, stream_ptr(x.device)),
+          'fd_ff_geglu')
     count_launch()
-    return out.reshape(*x.shape[:-1], F2 // 2)
+    return out if stride else out.reshape(*x.shape[:-1], F2 // 2)
 
 
 def ff_geglu_supported(K: int, F: int) -> bool:

@@ -248,12 +248,15 @@ k13_ff_geglu_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_const
 }  // namespace fd
 
 extern "C" int fd_ff_geglu(const void* x_bf16_dev, const void* w_bf16_dev, const void* bias_bf16_dev, void* out_bf16_dev,
-                           int M, int F, int K, void* stream) {
+                           int M, int F, int K, int64_t out_row_stride, void* stream) {
   using namespace fd;
   FD_REQUIRE(x_bf16_dev && w_bf16_dev && bias_bf16_dev && out_bf16_dev, "fd_ff_geglu: NULL pointer");
   FD_REQUIRE(M > 0 && F > 0 && K > 0, "fd_ff_geglu: non-positive shape %d %d %d", M, F, K);
   FD_REQUIRE(K % G_BK == 0, "fd_ff_geglu: K=%d must be a multiple of %d", K, G_BK);
   FD_REQUIRE(F % G_BF == 0, "fd_ff_geglu: F=%d (features per half) must be a multiple of %d", F, G_BF);
+  if (out_row_stride <= 0) out_row_stride = F;
+  FD_REQUIRE(out_row_stride >= F && out_row_stride % 8 == 0, "fd_ff_geglu: output row stride %lld must be a multiple of 8 and >= F",
+             static_cast<long long>(out_row_stride));
   FD_REQUIRE(reinterpret_cast<uintptr_t>(x_bf16_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(w_bf16_dev) % 16 == 0 &&
                  reinterpret_cast<uintptr_t>(out_bf16_dev) % 16 == 0 && reinterpret_cast<uintptr_t>(bias_bf16_dev) % 2 == 0,
              "fd_ff_geglu: x / w / out must be 16-byte aligned");
@@ -276,7 +279,7 @@ extern "C" int fd_ff_geglu(const void* x_bf16_dev, const void* w_bf16_dev, const
   }
   {
     uint64_t dims[2] = {static_cast<uint64_t>(F), static_cast<uint64_t>(M)};
-    uint64_t strides[1] = {static_cast<uint64_t>(F) * 2};
+    uint64_t strides[1] = {static_cast<uint64_t>(out_row_stride) * 2};
     uint32_t box[2] = {64, G_BM};
     rc = encode_tmap(&tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out_bf16_dev, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != FD_OK) return rc;

@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(256) k8_add_layernorm_kernel(const uint32_t* _
                                                                const uint32_t* __restrict__ gamma,
                                                                const uint32_t* __restrict__ beta,
                                                                uint32_t* __restrict__ sum_out,
-                                                               uint32_t* __restrict__ norm_out, int64_t M, float eps) {
+                                                               uint32_t* __restrict__ norm_out, int64_t M, float eps,
+                                                               int64_t sum_stride_pairs) {
   constexpr int PAIRS = PAIRS_PER_LANE * 32;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(256) k8_add_layernorm_kernel(const uint32_t* _
       // the residual stream is bf16: normalise exactly what is stored
       __nv_bfloat162 r = __floats2bfloat162_rn(v[i].x + t.x, v[i].y + t.y);
       const uint32_t rb = *reinterpret_cast<uint32_t*>(&r);
-      if (sum_out) sum_out[row * PAIRS + lane + 32 * i] = rb;
+      if (sum_out) sum_out[row * sum_stride_pairs + lane + 32 * i] = rb;
       v[i] = bf2_to_f2(rb);
     }
     s += v[i].x + v[i].y;
@@ -632,11 +633,15 @@ extern "C" int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_d
 
 extern "C" int fd_add_layernorm(const void* x_bf16_dev, const void* y_bf16_dev, const void* gamma_bf16_dev,
                                 const void* beta_bf16_dev, void* sum_out_bf16_dev, void* norm_out_bf16_dev,
-                                int64_t M, int C, float eps, void* stream) {
+                                int64_t M, int C, float eps, int64_t sum_out_row_stride, void* stream) {
   using namespace fd;
   FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && norm_out_bf16_dev, "fd_add_layernorm: NULL pointer");
   FD_REQUIRE(M > 0 && (C == 320 || C == 640 || C == 1280), "fd_add_layernorm: need M > 0 and C in {320, 640, 1280}");
   FD_REQUIRE(!sum_out_bf16_dev || y_bf16_dev, "fd_add_layernorm: sum_out without y");
+  if (sum_out_row_stride <= 0) sum_out_row_stride = C;
+  FD_REQUIRE(sum_out_row_stride >= C && sum_out_row_stride % 2 == 0, "fd_add_layernorm: sum_out row stride %lld must be even and >= C",
+             static_cast<long long>(sum_out_row_stride));
+  const int64_t ssp = sum_out_row_stride / 2;
   int rc = check_device();
   if (rc != FD_OK) return rc;
   const unsigned grid = static_cast<unsigned>((M + 7) / 8);
@@ -644,9 +649,9 @@ extern "C" int fd_add_layernorm(const void* x_bf16_dev, const void* y_bf16_dev, 
   auto X = static_cast<const uint32_t*>(x_bf16_dev), Y = static_cast<const uint32_t*>(y_bf16_dev);
   auto Gm = static_cast<const uint32_t*>(gamma_bf16_dev), Bt = static_cast<const uint32_t*>(beta_bf16_dev);
   auto So = static_cast<uint32_t*>(sum_out_bf16_dev), No = static_cast<uint32_t*>(norm_out_bf16_dev);
-  if (C == 320) k8_add_layernorm_kernel<5><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
-  else if (C == 640) k8_add_layernorm_kernel<10><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
-  else k8_add_layernorm_kernel<20><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps);
+  if (C == 320) k8_add_layernorm_kernel<5><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps, ssp);
+  else if (C == 640) k8_add_layernorm_kernel<10><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps, ssp);
+  else k8_add_layernorm_kernel<20><<<grid, 256, 0, st>>>(X, Y, Gm, Bt, So, No, M, eps, ssp);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
 }

@@ -211,6 +211,7 @@ class CrossAttention(nn.Module):
 
 
 FF_GEGLU_FUSED = True   # K13 on / off (off = cuBLAS projection + K6); profiles/time_unet.py A/Bs the two
+MERGED_OUT_GEMM = os.environ.get('FD_MERGED_OUT', '1') != '0'   # ff.net[2] + residual + proj_out as one K = 5C GEMM (needs K13)
 
 
 class GEGLU(nn.Module):
@@ -249,16 +250,29 @@ class BasicTransformerBlock(nn.Module):
         self.norm2 = nn.LayerNorm(dim)
         self.norm3 = nn.LayerNorm(dim)
 
-    def forward(self, x, kv, ctx_index):
+    def forward(self, x, kv, ctx_index, merged_out=None):
         # K8: each residual add is fused with the LayerNorm that feeds the next branch
         ln = _native.add_layernorm
         if not x.is_contiguous():
             x = x.contiguous()
         _, n = ln(x, None, self.norm1.weight, self.norm1.bias, self.norm1.eps)
         x, n = ln(x, self.attn1(n), self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        x, n = ln(x, self.attn2(n, kv, ctx_index), self.norm3.weight, self.norm3.bias,
-                  self.norm3.eps)
-        return self.ff(n) + x
+        if merged_out is None:
+            x, n = ln(x, self.attn2(n, kv, ctx_index), self.norm3.weight, self.norm3.bias, self.norm3.eps)
+            return self.ff(n) + x
+        # Merged output GEMM (see SpatialTransformer._merged_out): the block's tail
+        #     y = x3 + W2 h + b2 ,  p = Wo y + bo            (ff.net[2], residual add, proj_out)
+        # is the single GEMM  p = [h | x3] [Wo W2 | Wo]^T + (Wo b2 + bo)  over K = 5C: K13 writes h = GEGLU(n3) into the left
+        # 4C columns of one [M, 5C] buffer and K8 the residual stream x3 into the right C columns, so neither the second
+        # feed-forward GEMM nor the add exists (2 launches fewer per block).
+        w_m, b_m = merged_out
+        B, N, C = x.shape
+        buf = torch.empty((B * N, 5 * C), dtype=x.dtype, device=x.device)
+        _, n = ln(x, self.attn2(n, kv, ctx_index), self.norm3.weight, self.norm3.bias, self.norm3.eps,
+                  sum_out=buf[:, 4 * C:])
+        proj = self.ff.net[0].proj
+        _native.ff_geglu(n.reshape(B * N, C), proj.weight, proj.bias, out=buf[:, :4 * C])
+        return F.linear(buf, w_m, b_m).view(B, N, C)
 
 
 class SpatialTransformer(nn.Module):
@@ -270,14 +284,38 @@ class SpatialTransformer(nn.Module):
             [BasicTransformerBlock(ch, heads, ctx_dim)])
         self.proj_out = nn.Conv2d(ch, ch, 1)
 
+    def _merged_out(self):
+        '''[C, 5C] weight [Wo W2 | Wo] and bias Wo b2 + bo of the merged output GEMM (products in fp32, stored in the model
+        dtype), cached until ff.net[2] or proj_out changes.  Only for a single transformer block whose GEGLU runs on K13.'''
+        blk = self.transformer_blocks[0]
+        lin2, po = blk.ff.net[2], self.proj_out
+        ps = (lin2.weight, lin2.bias, po.weight, po.bias)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cached = self.__dict__.get('_merged_cache')
+        if cached is None or cached[0] != key:
+            C = po.out_channels
+            wo = po.weight.detach().reshape(C, C).float()
+            w_m = torch.cat([wo @ lin2.weight.detach().float(), wo], dim=1).to(po.weight.dtype).contiguous()
+            b_m = (wo @ lin2.bias.detach().float() + po.bias.detach().float()).to(po.weight.dtype)
+            cached = (key, (w_m, b_m), ps)
+            self.__dict__['_merged_cache'] = cached
+        return cached[1]
+
     def forward(self, x, kv, ctx_index):
         B, C, H, W = x.shape
         # proj_in / proj_out are 1x1 convolutions: run them as GEMMs on the token matrix
         h = _gn(x, self.norm, silu=False).permute(0, 2, 3, 1).reshape(B, H * W, C)
         h = F.linear(h, self.proj_in.weight.reshape(C, C), self.proj_in.bias)
-        for blk in self.transformer_blocks:
-            h = blk(h, kv, ctx_index)
-        h = F.linear(h, self.proj_out.weight.reshape(C, C), self.proj_out.bias)
+        blk0 = self.transformer_blocks[0]
+        if (MERGED_OUT_GEMM and FF_GEGLU_FUSED and len(self.transformer_blocks) == 1 and h.is_cuda
+                and h.dtype == torch.bfloat16 and _native.ff_geglu_supported(C, 4 * C)
+                and blk0.ff.net[0].proj.bias is not None and blk0.ff.net[2].bias is not None
+                and self.proj_out.bias is not None):
+            h = blk0(h, kv, ctx_index, merged_out=self._merged_out())   # already proj_out's output
+        else:
+            for blk in self.transformer_blocks:
+                h = blk(h, kv, ctx_index)
+            h = F.linear(h, self.proj_out.weight.reshape(C, C), self.proj_out.bias)
         return h.reshape(B, H, W, C).permute(0, 3, 1, 2) + x
 
 
@@ -487,6 +525,9 @@ class UNet2DConditionModel(nn.Module):
         for m in self.modules():
             if isinstance(m, ResnetBlock2D):
                 ps += [m.time_emb_proj.weight, m.time_emb_proj.bias, m.conv1.bias]
+            elif isinstance(m, SpatialTransformer):   # the merged output GEMM's weight is derived from these
+                lin2 = m.transformer_blocks[0].ff.net[2]
+                ps += [lin2.weight, lin2.bias, m.proj_out.weight, m.proj_out.bias]
         return tuple((p.data_ptr(), p._version) for p in ps)
 
     def invalidate_derived(self):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FD_ABI_VERSION 3
+#define FD_ABI_VERSION 4
 
 /* error codes */
 #define FD_OK            0
@@ -263,8 +263,10 @@ int fd_attention_f32(const float* q_dev, const float* k_dev, const float* v_dev,
 int fd_ff_geglu(const void* x_bf16_dev,     /* [M, K] bf16 row-major tokens                     */
                 const void* w_bf16_dev,     /* [2F, K] bf16: value rows, then gate rows           */
                 const void* bias_bf16_dev,  /* [2F] bf16                                          */
-                void*       out_bf16_dev,   /* [M, F] bf16                                        */
+                void*       out_bf16_dev,   /* [M, F] bf16 (rows out_row_stride elements apart)    */
                 int M, int F, int K,        /* F % 128 == 0, K % 64 == 0                          */
+                int64_t out_row_stride,     /* 0 = F; % 8 == 0: the output may be a column block   *
+                                             * of a wider matrix (see UNet "merged output GEMM")    */
                 void* stream);
 
 /* ---- K2: cross-attention K/V projection of the fixed context, hoisted out of the loop *
@@ -370,7 +372,11 @@ int fd_add_layernorm(const void* x_bf16_dev,       /* [M, C]                    
                      const void* gamma_bf16_dev, const void* beta_bf16_dev,   /* [C]          */
                      void* sum_out_bf16_dev,       /* [M, C] x + y, or NULL                   */
                      void* norm_out_bf16_dev,      /* [M, C]                                  */
-                     int64_t M, int C, float eps, void* stream);
+                     int64_t M, int C, float eps,
+                     int64_t sum_out_row_stride,   /* elements between rows of sum_out (0 = C):
+                                                      the sum may land in a column block of a
+                                                      wider matrix                             */
+                     void* stream);
 
 /* diffusers GEGLU: out[m, f] = in[m, f] * gelu(in[m, F + f]), exact (erf) GELU.           */
 int fd_geglu(const void* in_bf16_dev,            /* [M, 2F]                                 */

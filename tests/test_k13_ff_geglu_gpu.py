@@ -29,6 +29,10 @@ def test_ff_geglu_matches_fp32(native, cuda_dev, M, C):
     # leading batch dims
     got3 = native.ff_geglu(x.view(2, M // 2, C), w, b)
     assert torch.equal(got3.view(M, 4 * C), got)
+    # output as the left column block of a wider matrix (the merged output GEMM's operand): same bits, the rest untouched
+    wide = torch.full((M, 5 * C), 3.0, device=cuda_dev).bfloat16()
+    assert native.ff_geglu(x, w, b, out=wide[:, :4 * C]).data_ptr() == wide.data_ptr()
+    assert torch.equal(wide[:, :4 * C], got) and (wide[:, 4 * C:] == 3.0).all()
 
 
 def test_ff_geglu_gate_range(native, cuda_dev):

@@ -119,3 +119,9 @@ def test_add_layernorm_matches_torch(native, cuda_dev, M, C, with_y):
     assert torch.equal(total, s)
     ref = F.layer_norm(s.float(), (C,), w.float(), b.float(), 1e-5)
     torch.testing.assert_close(norm.float(), ref, rtol=1e-2, atol=1e-2)
+    if with_y:   # the sum written into a column block of a wider matrix: same bits, nothing else touched
+        wide = torch.full((M, 5 * C), 7.0, device=cuda_dev).bfloat16()
+        total2, norm2 = native.add_layernorm(x, y, w, b, 1e-5, sum_out=wide[:, 4 * C:])
+        assert total2.data_ptr() == wide[:, 4 * C:].data_ptr()
+        assert torch.equal(wide[:, 4 * C:], s) and torch.equal(norm2, norm)
+        assert (wide[:, :4 * C] == 7.0).all()

@@ -51,8 +51,11 @@ def test_attn2_layers_match_oracle(native, cuda_dev, fp32_math, fused, monkeypat
         assert rel_l2(got, want) < ATTN_TOL, name
 
 
-@pytest.mark.parametrize('hw', [32, 64])
-def test_noise_prediction_matches_oracle(native, cuda_dev, fp32_math, hw):
+@pytest.mark.parametrize('hw,merged', [(32, True), (64, True), (32, False)])
+def test_noise_prediction_matches_oracle(native, cuda_dev, fp32_math, hw, merged, monkeypatch):
+    '''`merged`: ff.net[2] + residual + proj_out as the one K = 5C GEMM (the default) or as the separate launches.'''
+    from flexdiffuse_b200 import unet as unet_mod
+    monkeypatch.setattr(unet_mod, 'MERGED_OUT_GEMM', merged)
     unet, _, sd, _ = models(str(cuda_dev))
     g = torch.Generator(device=cuda_dev).manual_seed(hw)
     x = torch.randn(2, 4, hw, hw, device=cuda_dev, generator=g)
@@ -63,6 +66,36 @@ def test_noise_prediction_matches_oracle(native, cuda_dev, fp32_math, hw):
         assert torch.isfinite(got.float()).all()
         assert want.abs().mean() > 1e-3  # a degenerate (all ~0) output would prove nothing
         assert rel_l2(got, want) < EPS_TOL, (t, rel_l2(got, want))
+
+
+def test_merged_output_gemm_equals_separate_launches(native, cuda_dev, fp32_math, monkeypatch):
+    '''Every SpatialTransformer: [h | x3] [Wo W2 | Wo]^T + (Wo b2 + bo) against ff.net[2] -> add -> proj_out on the same
+    input, both against the fp32 evaluation of the same tail; the merged form must not be further from it than 1.5x the
+    separate one (it skips two bf16 roundings and adds the rounding of Wo W2).'''
+    from flexdiffuse_b200 import unet as unet_mod
+    unet, _, _, _ = models(str(cuda_dev))
+    g = torch.Generator(device=cuda_dev).manual_seed(5)
+    ctx = torch.randn(2, 77, 768, device=cuda_dev, generator=g)
+    kv = unet.build_kv_cache(ctx)
+    idx = torch.tensor([0, 1], dtype=torch.int32, device=cuda_dev)
+    sts = [m for m in unet.modules() if isinstance(m, unet_mod.SpatialTransformer)]
+    assert len(sts) == 16
+    for st in sts:
+        C = st.proj_out.out_channels
+        hw = {320: 32, 640: 16, 1280: 8}[C]
+        x = torch.randn(2, C, hw, hw, device=cuda_dev, generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+        outs = {}
+        for merged in (True, False):
+            monkeypatch.setattr(unet_mod, 'MERGED_OUT_GEMM', merged)
+            before = native.LAUNCHES
+            outs[merged] = st(x, kv, idx).float()
+            outs[merged, 'launches'] = native.LAUNCHES - before
+        assert rel_l2(outs[True], outs[False]) < 1e-2, C
+        w_m, b_m = st._merged_out()
+        lin2 = st.transformer_blocks[0].ff.net[2]
+        wo = st.proj_out.weight.reshape(C, C).double()
+        torch.testing.assert_close(w_m.double(), torch.cat([wo @ lin2.weight.double(), wo], 1), rtol=1e-2, atol=1e-3)
+        torch.testing.assert_close(b_m.double(), wo @ lin2.bias.double() + st.proj_out.bias.double(), rtol=1e-2, atol=1e-3)
 
 
 def test_cached_context_equals_inline_projection(native, cuda_dev):
