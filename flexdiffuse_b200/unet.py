@@ -285,7 +285,7 @@ class SpatialTransformer(nn.Module):
         self.proj_out = nn.Conv2d(ch, ch, 1)
 
     def _merged_out(self):
-        '''[C, 5C] weight [Wo W2 | Wo] and bias Wo b2 + bo of the merged output GEMM (products in fp32, stored in the model
+        '''[C, 5C] weight [Wo W2 | Wo] and bias Wo b2 + bo of the merged output GEMM (products in fp64, stored in the model
         dtype), cached until ff.net[2] or proj_out changes.  Only for a single transformer block whose GEGLU runs on K13.'''
         blk = self.transformer_blocks[0]
         lin2, po = blk.ff.net[2], self.proj_out
@@ -294,9 +294,9 @@ class SpatialTransformer(nn.Module):
         cached = self.__dict__.get('_merged_cache')
         if cached is None or cached[0] != key:
             C = po.out_channels
-            wo = po.weight.detach().reshape(C, C).float()
-            w_m = torch.cat([wo @ lin2.weight.detach().float(), wo], dim=1).to(po.weight.dtype).contiguous()
-            b_m = (wo @ lin2.bias.detach().float() + po.bias.detach().float()).to(po.weight.dtype)
+            wo = po.weight.detach().reshape(C, C).double()   # float64: independent of the TF32 matmul switch
+            w_m = torch.cat([wo @ lin2.weight.detach().double(), wo], dim=1).to(po.weight.dtype).contiguous()
+            b_m = (wo @ lin2.bias.detach().double() + po.bias.detach().double()).to(po.weight.dtype)
             cached = (key, (w_m, b_m), ps)
             self.__dict__['_merged_cache'] = cached
         return cached[1]
