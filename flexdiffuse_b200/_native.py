@@ -34,7 +34,7 @@ ABI_SYMBOLS = ('fd_version', 'fd_last_error_string', 'fd_arch_check',
                'fd_visual_projection_workspace_bytes', 'fd_visual_projection_range_flag',
                'fd_linear_x3_operand_bytes', 'fd_linear_x3_split', 'fd_linear_x3_split_ln', 'fd_linear_x3',
                'fd_linear_x3_flag',
-               'fd_attention_f32', 'fd_ff_geglu', 'fd_concat_channels', 'fd_upsample_nearest2x')
+               'fd_attention_f32', 'fd_ff_geglu', 'fd_concat_channels', 'fd_upsample_nearest2x', 'fd_add_groupnorm_act')
 
 
 class NativeError(RuntimeError):
@@ -131,6 +131,9 @@ def lib() -> C.CDLL:
         C.c_int, C.c_int64, vp
     ]
     l.fd_groupnorm_act.restype = C.c_int
+    l.fd_add_groupnorm_act.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                       C.c_int, vp]
+    l.fd_add_groupnorm_act.restype = C.c_int
     l.fd_add_layernorm.argtypes = [vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int,
                                    C.c_float, C.c_int64, vp]
     l.fd_add_layernorm.restype = C.c_int
@@ -453,6 +456,38 @@ def groupnorm_act(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
     check(rc, 'fd_groupnorm_act')
     count_launch(1 if x.numel() * 2 <= (8 << 20) else 3)  # cluster kernel or stats/finalize/apply
     return y
+
+
+def _gn_workspace(device, nbytes: int) -> torch.Tensor:
+    ws = _gn_workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _gn_retired.append(ws)  # a captured CUDA graph may still point at it
+        ws = torch.zeros(max(2 * nbytes, 1 << 24), dtype=torch.uint8, device=device)
+        _gn_workspaces[device] = ws
+    return ws
+
+
+def add_groupnorm_act(x: torch.Tensor, h: torch.Tensor, rbias: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                      groups: int, eps: float, silu: bool):
+    '''fd_add_groupnorm_act on channels-last bf16 [N,C,H,W] tensors: returns (x + h + rbias[c], act(GroupNorm(that))).'''
+    for name, t in (('x', x), ('h', h)):
+        if t.dtype != torch.bfloat16 or not t.is_cuda or t.dim() != 4:
+            raise NativeError(f'add_groupnorm_act: {name} must be a CUDA bfloat16 [N,C,H,W] tensor; no fallback')
+    if x.shape != h.shape:
+        raise NativeError('add_groupnorm_act: x / h shape mismatch')
+    if not x.is_contiguous(memory_format=torch.channels_last):
+        x = x.contiguous(memory_format=torch.channels_last)
+    if not h.is_contiguous(memory_format=torch.channels_last):
+        h = h.contiguous(memory_format=torch.channels_last)
+    _need(rbias, 'rbias', torch.bfloat16)
+    N, Cc, H, W = x.shape
+    total, y = torch.empty_like(x), torch.empty_like(x)
+    ws = _gn_workspace(x.device, lib().fd_groupnorm_act_workspace_bytes(N, H * W, Cc, groups))
+    check(lib().fd_add_groupnorm_act(ptr(x), ptr(h), ptr(rbias), ptr(total), ptr(gamma), ptr(beta), ptr(ws), ptr(y), N, H * W,
+                                     Cc, groups, float(eps), int(silu), stream_ptr(x.device)), 'fd_add_groupnorm_act')
+    count_launch(1 if x.numel() * 2 <= (8 << 20) else 4)
+    return total, y
 
 
 def geglu(x: torch.Tensor) -> torch.Tensor:

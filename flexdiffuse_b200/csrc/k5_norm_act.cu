@@ -200,6 +200,9 @@ __global__ void __launch_bounds__(512) k5_gn_vec_apply_kernel(const GnVecArgs a)
 // the groups, gamma, beta and bias of its 8 channels are fixed) and rows t / sv, + RP, ...
 struct GnClusterArgs {
   const __nv_bfloat16* x;
+  const __nv_bfloat16* h;        // optional residual branch: the kernel normalises s = bf16(x + (h + rbias[c])), K7's sum,
+  const __nv_bfloat16* rbias;    // and writes s to sum_out (fd_add_groupnorm_act: K7 folded into the GroupNorm that follows it)
+  __nv_bfloat16* sum_out;
   const __nv_bfloat16* bias;
   int64_t bias_stride;
   const __nv_bfloat16* gamma;
@@ -239,6 +242,7 @@ __device__ __forceinline__ void dsmem_st_f2(float2* local_ptr, uint32_t rank, fl
 constexpr int GN_MAX_GSET = 8;    // groups per cluster
 constexpr int GN_MAX_SV = 32;     // 16-byte vectors per pixel strip (<= 512 B)
 
+template <bool RES>   // RES: the residual branch (a.h) is summed in; rows go through in batches of 4 + 4 loads instead of 8
 __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClusterArgs a) {
   extern __shared__ uint4 slab[];                      // [rows_per_cta][sv]
   __shared__ float2 s_col[GN_THREADS * 4];             // [RP][sv * 4] pair-column partials, tree-reduced over RP
@@ -261,21 +265,47 @@ __global__ void __launch_bounds__(GN_THREADS) k5_gn_cluster_kernel(const GnClust
   const uint4* xb = reinterpret_cast<const uint4*>(a.x) + gbase;
 
   float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float rb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const uint4* hb = RES ? reinterpret_cast<const uint4*>(a.h) + gbase : nullptr;
+  uint4* sb = RES ? reinterpret_cast<uint4*>(a.sum_out) + gbase : nullptr;
   uint4 gam_raw = make_uint4(0, 0, 0, 0), bet_raw = gam_raw;
   if (active) {
     if (a.bias) unpack8(reinterpret_cast<const uint4*>(a.bias + static_cast<size_t>(n) * a.bias_stride)[vec0], b);
+    if (RES) unpack8(reinterpret_cast<const uint4*>(a.rbias)[vec0], rb);
     gam_raw = reinterpret_cast<const uint4*>(a.gamma)[vec0];  // needed after the statistics
     bet_raw = reinterpret_cast<const uint4*>(a.beta)[vec0];
   }
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (active) {
-    for (int r = rr; r < rows; r += 8 * RP) {  // up to eight rows in flight
-      uint4 v[8];
+    constexpr int U = RES ? 4 : 8;
+    for (int r = rr; r < rows; r += U * RP) {  // up to eight loads in flight
+      uint4 v[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < U; ++u)
         if (r + u * RP < rows) v[u] = xb[static_cast<size_t>(r + u * RP) * vec_per_row];
+      if constexpr (RES) {   // s = bf16(x + (h + rbias)), exactly K7's arithmetic; s is what gets stored, normalised and kept in the slab
+        uint4 hv[U];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < U; ++u)
+          if (r + u * RP < rows) hv[u] = hb[static_cast<size_t>(r + u * RP) * vec_per_row];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (r + u * RP < rows) {
+            float fx[8], fh[8];
+            unpack8(v[u], fx);
+            unpack8(hv[u], fh);
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 p2 = __floats2bfloat162_rn(fx[2 * k] + (fh[2 * k] + rb[2 * k]), fx[2 * k + 1] + (fh[2 * k + 1] + rb[2 * k + 1]));
+              o[k] = *reinterpret_cast<uint32_t*>(&p2);
+            }
+            v[u] = make_uint4(o[0], o[1], o[2], o[3]);
+            sb[static_cast<size_t>(r + u * RP) * vec_per_row] = v[u];
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
         if (r + u * RP < rows) {
           slab[(r + u * RP) * sv + j] = v[u];
           float f[8];
@@ -502,12 +532,17 @@ extern "C" int64_t fd_groupnorm_act_workspace_bytes(int N, int HW, int C, int G)
   return (static_cast<int64_t>(N) * fd::GN_VEC_MAX_SLABS * G + static_cast<int64_t>(N) * G) * 8;
 }
 
-extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
-                                const void* beta_bf16_dev, void* workspace_dev, void* y_bf16_dev, int N, int HW,
-                                int C, int G, float eps, int act_silu, int64_t bias_row_stride, void* stream) {
+extern "C" int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev, const void* bias_bf16_dev,
+                                    void* y_bf16_dev, int64_t n_elem, int C, void* stream);
+
+static int fd_groupnorm_impl(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
+                             const void* beta_bf16_dev, void* workspace_dev, void* y_bf16_dev, int N, int HW,
+                             int C, int G, float eps, int act_silu, int64_t bias_row_stride, void* stream,
+                             const void* h_bf16_dev, const void* rbias_bf16_dev, void* sum_out_bf16_dev) {
   using namespace fd;
   FD_REQUIRE(x_bf16_dev && gamma_bf16_dev && beta_bf16_dev && workspace_dev && y_bf16_dev,
              "fd_groupnorm_act: NULL pointer");
+  int rc = FD_OK;
   FD_REQUIRE(N > 0 && HW > 0 && C > 0, "fd_groupnorm_act: non-positive shape");
   FD_REQUIRE(G > 0 && G <= GN_MAX_GROUPS && C % G == 0 && (C / G) % 2 == 0 && C % 64 == 0 && C <= 4096,
              "fd_groupnorm_act: need G <= %d, C %% G == 0, even channels per group, C %% 64 == 0, C <= 4096 (C=%d G=%d)",
@@ -519,7 +554,7 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
              "fd_groupnorm_act: x / y / gamma / beta must be 16-byte aligned, workspace 8-byte aligned");
   FD_REQUIRE(!bias_bf16_dev || (bias_row_stride >= C && bias_row_stride % 8 == 0 && !mis16(bias_bf16_dev)),
              "fd_groupnorm_act: bias row stride must be a multiple of 8 and >= C, pointer 16-byte aligned");
-  int rc = check_device();
+  rc = check_device();
   if (rc != FD_OK) return rc;
   const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x_bf16_dev);
   const __nv_bfloat16* bp = static_cast<const __nv_bfloat16*>(bias_bf16_dev);
@@ -557,13 +592,17 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
       if (smem <= 96 * 1024 && n_sets * cl <= 0x7fffffff) {
         GnClusterArgs c;
         c.x = xp; c.bias = bp; c.bias_stride = bias_row_stride; c.gamma = gp; c.beta = tp; c.y = yp;
+        c.h = static_cast<const __nv_bfloat16*>(h_bf16_dev);
+        c.rbias = static_cast<const __nv_bfloat16*>(rbias_bf16_dev);
+        c.sum_out = static_cast<__nv_bfloat16*>(sum_out_bf16_dev);
         c.HW = HW; c.C = C; c.G = G; c.rows_per_cta = rows_per_cta; c.gset = gset; c.sv = sv; c.eps = eps;
         c.act_silu = act_silu;
         static thread_local int attr_device = -1;
         int dev = 0;
         FD_CUDA_OK(cudaGetDevice(&dev));
         if (attr_device != dev) {
-          FD_CUDA_OK(cudaFuncSetAttribute(k5_gn_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+          FD_CUDA_OK(cudaFuncSetAttribute(k5_gn_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+          FD_CUDA_OK(cudaFuncSetAttribute(k5_gn_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
           attr_device = dev;
         }
         cudaLaunchConfig_t cfg = {};
@@ -578,12 +617,18 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k5_gn_cluster_kernel, c));
+        if (c.h) FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k5_gn_cluster_kernel<true>, c));
+        else FD_CUDA_OK(cudaLaunchKernelEx(&cfg, k5_gn_cluster_kernel<false>, c));
         return FD_OK;
       }
     }
   }
-  // streaming path
+  // streaming path (a residual branch is summed by K7 first: three more launches follow anyway)
+  if (h_bf16_dev) {
+    rc = fd_add_bias_residual(x_bf16_dev, h_bf16_dev, rbias_bf16_dev, sum_out_bf16_dev, static_cast<int64_t>(N) * HW * C, C, stream);
+    if (rc != FD_OK) return rc;
+    xp = static_cast<const __nv_bfloat16*>(sum_out_bf16_dev);
+  }
   GnVecArgs v;
   v.x = xp; v.bias = bp; v.bias_stride = bias_row_stride; v.gamma = gp; v.beta = tp; v.y = yp;
   v.HW = HW; v.C = C; v.G = G; v.eps = eps; v.act_silu = act_silu;
@@ -606,6 +651,28 @@ extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_de
   k5_gn_vec_apply_kernel<<<grid, block, 0, st>>>(v);
   FD_CUDA_OK(cudaGetLastError());
   return FD_OK;
+}
+
+extern "C" int fd_groupnorm_act(const void* x_bf16_dev, const void* bias_bf16_dev, const void* gamma_bf16_dev,
+                                const void* beta_bf16_dev, void* workspace_dev, void* y_bf16_dev, int N, int HW,
+                                int C, int G, float eps, int act_silu, int64_t bias_row_stride, void* stream) {
+  return fd_groupnorm_impl(x_bf16_dev, bias_bf16_dev, gamma_bf16_dev, beta_bf16_dev, workspace_dev, y_bf16_dev, N, HW, C, G, eps,
+                           act_silu, bias_row_stride, stream, nullptr, nullptr, nullptr);
+}
+
+// s = x + h + rbias[c] (K7) and y = act(GroupNorm(s)) in one launch where the cluster kernel applies (else K7 + the
+// streaming GroupNorm): a resnet's residual add folded into the GroupNorm of the block that consumes its output.
+extern "C" int fd_add_groupnorm_act(const void* x_bf16_dev, const void* h_bf16_dev, const void* rbias_bf16_dev,
+                                    void* sum_out_bf16_dev, const void* gamma_bf16_dev, const void* beta_bf16_dev,
+                                    void* workspace_dev, void* y_bf16_dev, int N, int HW, int C, int G, float eps,
+                                    int act_silu, void* stream) {
+  using namespace fd;
+  FD_REQUIRE(h_bf16_dev && rbias_bf16_dev && sum_out_bf16_dev, "fd_add_groupnorm_act: NULL pointer");
+  auto mis16 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 != 0; };
+  FD_REQUIRE(!mis16(h_bf16_dev) && !mis16(rbias_bf16_dev) && !mis16(sum_out_bf16_dev),
+             "fd_add_groupnorm_act: h / rbias / sum_out must be 16-byte aligned");
+  return fd_groupnorm_impl(x_bf16_dev, nullptr, gamma_bf16_dev, beta_bf16_dev, workspace_dev, y_bf16_dev, N, HW, C, G, eps,
+                           act_silu, 0, stream, h_bf16_dev, rbias_bf16_dev, sum_out_bf16_dev);
 }
 
 extern "C" int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev, const void* bias_bf16_dev,

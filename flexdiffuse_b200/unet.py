@@ -115,7 +115,9 @@ class ResnetBlock2D(nn.Module):
             self.__dict__['_tb_cache'] = cached
         return cached[1]
 
-    def forward(self, x, temb_act):
+    def forward(self, x, temb_act, next_norm: Optional[nn.GroupNorm] = None, next_silu: bool = False):
+        '''`next_norm`: the GroupNorm that consumes this block's output (a SpatialTransformer's `norm`, the next resnet's
+        `norm1`): the residual add (K7) is then folded into that GroupNorm's launch and the call returns (y, act(GN(y))).'''
         # K5: GroupNorm + SiLU in one NHWC pass.  cuDNN adds a convolution bias with a separate
         # broadcast kernel, so conv1's bias rides along with the time embedding into norm2 (K5's
         # per-(n,c) bias) and conv2's bias is folded into the residual add (K7).
@@ -128,6 +130,12 @@ class ResnetBlock2D(nn.Module):
                      padding=1)
         if self.conv_shortcut is not None:
             x = _conv1x1(x, self.conv_shortcut)
+        if next_norm is not None:
+            if FUSED_ADD_GN:
+                return _native.add_groupnorm_act(x, h, self.conv2.bias, next_norm.weight, next_norm.bias, next_norm.num_groups,
+                                                 next_norm.eps, next_silu)
+            y = _native.add_bias_residual(x, h, self.conv2.bias)
+            return y, _gn(y, next_norm, silu=next_silu)
         return _native.add_bias_residual(x, h, self.conv2.bias)
 
 
@@ -211,6 +219,7 @@ class CrossAttention(nn.Module):
 
 
 FF_GEGLU_FUSED = True   # K13 on / off (off = cuBLAS projection + K6); profiles/time_unet.py A/Bs the two
+FUSED_ADD_GN = os.environ.get('FD_FUSED_ADD_GN', '1') != '0'   # a resnet's residual add inside the GroupNorm launch that follows it
 MERGED_OUT_GEMM = os.environ.get('FD_MERGED_OUT', '1') != '0'   # ff.net[2] + residual + proj_out as one K = 5C GEMM (needs K13)
 
 
@@ -301,10 +310,11 @@ class SpatialTransformer(nn.Module):
             self.__dict__['_merged_cache'] = cached
         return cached[1]
 
-    def forward(self, x, kv, ctx_index):
+    def forward(self, x, kv, ctx_index, normed=None):
+        '''`normed`: GroupNorm(x) when the producer of x already computed it (ResnetBlock2D(next_norm=self.norm)).'''
         B, C, H, W = x.shape
         # proj_in / proj_out are 1x1 convolutions: run them as GEMMs on the token matrix
-        h = _gn(x, self.norm, silu=False).permute(0, 2, 3, 1).reshape(B, H * W, C)
+        h = (normed if normed is not None else _gn(x, self.norm, silu=False)).permute(0, 2, 3, 1).reshape(B, H * W, C)
         h = F.linear(h, self.proj_in.weight.reshape(C, C), self.proj_in.bias)
         blk0 = self.transformer_blocks[0]
         if (MERGED_OUT_GEMM and FF_GEGLU_FUSED and len(self.transformer_blocks) == 1 and h.is_cuda
@@ -378,9 +388,11 @@ class DownBlock(nn.Module):
     def forward(self, x, temb, kv, ctx_index):
         outs = []
         for i, res in enumerate(self.resnets):
-            x = res(x, temb)
             if self.attentions is not None:
-                x = self.attentions[i](x, kv, ctx_index)
+                x, z = res(x, temb, next_norm=self.attentions[i].norm)
+                x = self.attentions[i](x, kv, ctx_index, normed=z)
+            else:
+                x = res(x, temb)
             outs.append(x)
         if self.downsamplers is not None:
             x = self.downsamplers[0](x)
@@ -399,8 +411,8 @@ class MidBlock(nn.Module):
             [SpatialTransformer(ch, heads, ctx_dim, groups)])
 
     def forward(self, x, temb, kv, ctx_index):
-        x = self.resnets[0](x, temb)
-        x = self.attentions[0](x, kv, ctx_index)
+        x, z = self.resnets[0](x, temb, next_norm=self.attentions[0].norm)
+        x = self.attentions[0](x, kv, ctx_index, normed=z)
         return self.resnets[1](x, temb)
 
 
@@ -423,9 +435,11 @@ class UpBlock(nn.Module):
 
     def forward(self, x, skips: List[torch.Tensor], temb, kv, ctx_index):
         for i, res in enumerate(self.resnets):
-            x = res(_cat_skip(x, skips.pop()), temb)
             if self.attentions is not None:
-                x = self.attentions[i](x, kv, ctx_index)
+                x, z = res(_cat_skip(x, skips.pop()), temb, next_norm=self.attentions[i].norm)
+                x = self.attentions[i](x, kv, ctx_index, normed=z)
+            else:
+                x = res(_cat_skip(x, skips.pop()), temb)
         if self.upsamplers is not None:
             x = self.upsamplers[0](x)
         return x

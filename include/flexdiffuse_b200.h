@@ -345,6 +345,16 @@ int fd_groupnorm_act(const void* x_bf16_dev,     /* [N, HW, C] channels-last act
                      int64_t bias_row_stride,    /* elements between bias rows (>= C, even) */
                      void* stream);
 
+/* K7 folded into the K5 that consumes its result: sum_out = x + h + rbias[c] (ResnetBlock2D's residual add, as
+ * fd_add_bias_residual) and y = act(GroupNorm(sum_out) * gamma + beta) (the `norm` of the SpatialTransformer or the `norm1`
+ * of the ResnetBlock2D that follows) in ONE launch where the cluster kernel applies; otherwise K7 + the streaming
+ * GroupNorm.  Same arguments as fd_groupnorm_act without the per-(n, c) bias.                                              */
+int fd_add_groupnorm_act(const void* x_bf16_dev, const void* h_bf16_dev,   /* [N, HW, C] each            */
+                         const void* rbias_bf16_dev,                       /* [C]                        */
+                         void* sum_out_bf16_dev,                           /* [N, HW, C]                 */
+                         const void* gamma_bf16_dev, const void* beta_bf16_dev, void* workspace_dev,
+                         void* y_bf16_dev, int N, int HW, int C, int G, float eps, int act_silu, void* stream);
+
 /* y = x + h + bias[c]: ResnetBlock2D's residual add with conv2's bias folded in (NHWC bf16).
  * h == NULL: y = x + bias[c] (the bias of conv_in / Downsample2D / Upsample2D convolutions); y may alias x. */
 int fd_add_bias_residual(const void* x_bf16_dev, const void* h_bf16_dev /* or NULL */,

@@ -96,6 +96,23 @@ def test_upsample_nearest2x_equals_interpolate(native, cuda_dev, N, C, H, W):
     assert torch.equal(y, F.interpolate(x, scale_factor=2.0, mode='nearest'))
 
 
+@pytest.mark.parametrize('N,C,H,silu', [(2, 320, 64, False), (2, 640, 32, True), (2, 1280, 8, False), (4, 960, 16, True),
+                                        (16, 320, 64, False)])   # the last one takes the streaming path (K7 + three launches)
+def test_add_groupnorm_equals_k7_then_k5(native, cuda_dev, N, C, H, silu):
+    '''fd_add_groupnorm_act == fd_add_bias_residual followed by fd_groupnorm_act, bit for bit (sum and normalised output).'''
+    g = torch.Generator(device=cuda_dev).manual_seed(N * C + H)
+    mk = lambda: (torch.randn(N, C, H, H, device=cuda_dev, generator=g) * 1.5).bfloat16().contiguous(memory_format=torch.channels_last)
+    x, h = mk(), mk()
+    rb = (torch.randn(C, device=cuda_dev, generator=g) * 0.3).bfloat16()
+    gam = (torch.randn(C, device=cuda_dev, generator=g) * 0.3 + 1).bfloat16()
+    bet = (torch.randn(C, device=cuda_dev, generator=g) * 0.2).bfloat16()
+    y_ref = native.add_bias_residual(x, h, rb)
+    z_ref = native.groupnorm_act(y_ref, gam, bet, 32, 1e-6, silu)
+    y, z = native.add_groupnorm_act(x, h, rb, gam, bet, 32, 1e-6, silu)
+    assert torch.equal(y, y_ref)
+    assert torch.equal(z, z_ref)
+
+
 def test_groupnorm_is_bit_reproducible(native, cuda_dev):
     x = torch.randn(2, 640, 32, 32, device=cuda_dev).bfloat16() \
         .contiguous(memory_format=torch.channels_last)
